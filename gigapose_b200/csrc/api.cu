@@ -1,0 +1,464 @@
+// C-ABI layer of libgigapose_b200.so (see include/gigapose_b200.h): handle, memory carving, TMA descriptors and the
+// launch sequence for each entry point.  No device memory is allocated here; no call synchronises the host
+// (except the explicit diagnostics helper gp_time_sim_kernel).
+#include "../../include/gigapose_b200.h"
+#include "gigapose_kernels.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define GP_CUDA(expr)                                                                                     \
+  do {                                                                                                    \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess) return fail(GP_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));     \
+  } while (0)
+
+constexpr size_t kAlign = 1024;
+inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+
+// bump allocator over caller memory; with base == nullptr it only measures
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(static_cast<uint8_t*>(b)) {}
+  template <typename T>
+  T* take(size_t count) {
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += align_up(count * sizeof(T));
+    return p;
+  }
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 plane [rows, 1024] (K contiguous); box = 32 columns (64 B, SWIZZLE_64B) x 256 rows = one patch set
+int make_plane_map(CUtensorMap* map, void* ptr, uint64_t rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(GP_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from this driver");
+  cuuint64_t dims[2] = {GP_AE_DIM, rows};
+  cuuint64_t strides[1] = {GP_AE_DIM * sizeof(uint16_t)};
+  cuuint32_t box[2] = {32, 256};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return GP_OK;
+}
+
+struct Bank {
+  uint16_t *hi, *lo;      // [O*T*256, 1024]
+  float* mask16;          // [O*T, 256]
+  float* ist;             // [O*T, 256, 256] patch-major
+  float *K, *M, *pose;    // [O,9], [O,Tg,9], [O,Tg,16]
+};
+
+struct Workspace {
+  uint16_t *q_hi, *q_lo;  // [Bm*256, 1024]
+  float* q_mask16;        // [Bm,256]
+  float* q_ist;           // [Bm,256,256] patch-major
+  int *perm, *q_obj;      // [Bm]
+  float* sim_avg;         // [Bm,T]
+  float* rec_score;       // [Bm,T,256]
+  uint8_t *rec_idx, *rec_valid;
+  // local candidates
+  float* c_score; int* c_id; float* c_pts_score; uint8_t *c_idx, *c_valid;
+  // IST MLP scratch
+  int* row_count; int* row_ids; float *hidden1, *hidden2;
+};
+
+void carve_bank(Carver& c, const gp_config_t& cfg, Bank* b) {
+  const size_t OT = (size_t)cfg.num_objects * cfg.num_templates;
+  const size_t OTg = (size_t)cfg.num_objects * cfg.num_templates_global;
+  Bank tmp;
+  tmp.hi = c.take<uint16_t>(OT * GP_NUM_PATCHES * GP_AE_DIM);
+  tmp.lo = c.take<uint16_t>(OT * GP_NUM_PATCHES * GP_AE_DIM);
+  tmp.mask16 = c.take<float>(OT * GP_NUM_PATCHES);
+  tmp.ist = c.take<float>(OT * GP_NUM_PATCHES * GP_IST_DIM);
+  tmp.K = c.take<float>((size_t)cfg.num_objects * 9);
+  tmp.M = c.take<float>(OTg * 9);
+  tmp.pose = c.take<float>(OTg * 16);
+  if (b) *b = tmp;
+}
+
+void carve_workspace(Carver& c, const gp_config_t& cfg, Workspace* w) {
+  const size_t Bm = cfg.max_batch, T = cfg.num_templates, k = cfg.top_k;
+  Workspace tmp;
+  tmp.q_hi = c.take<uint16_t>(Bm * GP_NUM_PATCHES * GP_AE_DIM);
+  tmp.q_lo = c.take<uint16_t>(Bm * GP_NUM_PATCHES * GP_AE_DIM);
+  tmp.q_mask16 = c.take<float>(Bm * GP_NUM_PATCHES);
+  tmp.q_ist = c.take<float>(Bm * GP_NUM_PATCHES * GP_IST_DIM);
+  tmp.perm = c.take<int>(Bm);
+  tmp.q_obj = c.take<int>(Bm);
+  tmp.sim_avg = c.take<float>(Bm * T);
+  tmp.rec_score = c.take<float>(Bm * T * GP_NUM_PATCHES);
+  tmp.rec_idx = c.take<uint8_t>(Bm * T * GP_NUM_PATCHES);
+  tmp.rec_valid = c.take<uint8_t>(Bm * T * GP_NUM_PATCHES);
+  tmp.c_score = c.take<float>(Bm * k);
+  tmp.c_id = c.take<int>(Bm * k);
+  tmp.c_pts_score = c.take<float>(Bm * k * GP_NUM_PATCHES);
+  tmp.c_idx = c.take<uint8_t>(Bm * k * GP_NUM_PATCHES);
+  tmp.c_valid = c.take<uint8_t>(Bm * k * GP_NUM_PATCHES);
+  tmp.row_count = c.take<int>(1);
+  tmp.row_ids = c.take<int>(Bm * k * GP_NUM_PATCHES);
+  tmp.hidden1 = c.take<float>(Bm * k * GP_NUM_PATCHES * 1024);
+  tmp.hidden2 = c.take<float>(Bm * k * GP_NUM_PATCHES * 512);
+  if (w) *w = tmp;
+}
+
+int validate(const gp_config_t* cfg) {
+  if (!cfg) return fail(GP_ERR_INVALID, "null config");
+  if (cfg->abi_version != GP_ABI_VERSION) return fail(GP_ERR_INVALID, "ABI version mismatch: %d vs %d", cfg->abi_version, GP_ABI_VERSION);
+  if (cfg->num_objects < 1 || cfg->num_templates < 1 || cfg->max_batch < 1)
+    return fail(GP_ERR_INVALID, "num_objects, num_templates and max_batch must be >= 1");
+  if (cfg->top_k < 1 || cfg->top_k > 32) return fail(GP_ERR_INVALID, "top_k must be in [1,32]");
+  if (cfg->num_templates_global < cfg->num_templates) return fail(GP_ERR_INVALID, "num_templates_global < num_templates");
+  if (cfg->num_templates_global < cfg->top_k) return fail(GP_ERR_INVALID, "fewer templates than top_k (torch.topk would raise)");
+  if (cfg->template_id_stride < 1 || cfg->template_id_offset < 0) return fail(GP_ERR_INVALID, "bad template id stride/offset");
+  if (cfg->patch_size < 1) return fail(GP_ERR_INVALID, "patch_size must be >= 1");
+  if (cfg->precision != GP_PRECISION_FP32_SPLIT && cfg->precision != GP_PRECISION_BF16)
+    return fail(GP_ERR_INVALID, "unknown precision %d", cfg->precision);
+  if ((size_t)cfg->num_objects * cfg->num_templates * GP_NUM_PATCHES >= (1ull << 31))
+    return fail(GP_ERR_INVALID, "bank has too many rows for 32-bit TMA coordinates");
+  return GP_OK;
+}
+
+}  // namespace
+
+struct gp_context {
+  gp_config_t cfg;
+  int num_sms;
+  Bank bank;
+  Workspace ws;
+  CUtensorMap tm_q_hi, tm_q_lo, tm_t_hi, tm_t_lo;
+  gp::IstMlpWeights mlp;
+  bool mlp_set;
+  int cur_B;      // batch size staged by gp_set_queries (0 = none)
+};
+
+extern "C" {
+
+const char* gp_last_error(void) { return g_last_error.c_str(); }
+int gp_abi_version(void) { return GP_ABI_VERSION; }
+uint64_t gp_launch_count(void) { return g_launches.load(); }
+
+int gp_query_sizes(const gp_config_t* cfg, size_t* bank_bytes, size_t* workspace_bytes) {
+  if (int e = validate(cfg)) return e;
+  Carver cb(nullptr), cw(nullptr);
+  carve_bank(cb, *cfg, nullptr);
+  carve_workspace(cw, *cfg, nullptr);
+  if (bank_bytes) *bank_bytes = cb.off;
+  if (workspace_bytes) *workspace_bytes = cw.off;
+  return GP_OK;
+}
+
+int gp_create(const gp_config_t* cfg, void* bank_mem, void* workspace_mem, gp_handle_t* out) {
+  if (int e = validate(cfg)) return e;
+  if (!bank_mem || !workspace_mem || !out) return fail(GP_ERR_INVALID, "null pointer argument");
+  if (((uintptr_t)bank_mem | (uintptr_t)workspace_mem) & (kAlign - 1))
+    return fail(GP_ERR_INVALID, "bank and workspace must be %zu-byte aligned", kAlign);
+  GP_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  GP_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return fail(GP_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library contains sm_100a code only", cfg->device,
+                prop.major, prop.minor);
+  if ((int)prop.sharedMemPerBlockOptin < gp::sim_search_smem_bytes())
+    return fail(GP_ERR_UNSUPPORTED, "device offers %zu B of shared memory per block, kernel needs %d",
+                prop.sharedMemPerBlockOptin, gp::sim_search_smem_bytes());
+  gp_context* h = new (std::nothrow) gp_context();
+  if (!h) return fail(GP_ERR_INVALID, "out of host memory");
+  h->cfg = *cfg;
+  h->num_sms = prop.multiProcessorCount;
+  h->mlp_set = false;
+  h->cur_B = 0;
+  Carver cb(bank_mem), cw(workspace_mem);
+  carve_bank(cb, *cfg, &h->bank);
+  carve_workspace(cw, *cfg, &h->ws);
+  const uint64_t bank_rows = (uint64_t)cfg->num_objects * cfg->num_templates * GP_NUM_PATCHES;
+  const uint64_t q_rows = (uint64_t)cfg->max_batch * GP_NUM_PATCHES;
+  int e;
+  if ((e = make_plane_map(&h->tm_t_hi, h->bank.hi, bank_rows)) || (e = make_plane_map(&h->tm_t_lo, h->bank.lo, bank_rows)) ||
+      (e = make_plane_map(&h->tm_q_hi, h->ws.q_hi, q_rows)) || (e = make_plane_map(&h->tm_q_lo, h->ws.q_lo, q_rows))) {
+    delete h;
+    return e;
+  }
+  *out = h;
+  return GP_OK;
+}
+
+int gp_destroy(gp_handle_t h) {
+  delete h;
+  return GP_OK;
+}
+
+int gp_bank_write(gp_handle_t h, int obj, int tmpl0, int n, const float* feat, int feat_layout, int norm_passes,
+                  const float* mask, int H, int W, const float* ist_feat, void* stream) {
+  if (!h) return fail(GP_ERR_INVALID, "null handle");
+  const gp_config_t& c = h->cfg;
+  if (obj < 0 || obj >= c.num_objects || tmpl0 < 0 || n < 1 || tmpl0 + n > c.num_templates)
+    return fail(GP_ERR_INVALID, "template range [%d,%d) of object %d outside the bank (%d x %d)", tmpl0, tmpl0 + n, obj,
+                c.num_objects, c.num_templates);
+  if (!feat || !mask) return fail(GP_ERR_INVALID, "feat and mask are required");
+  if (H < 16 || W < 16) return fail(GP_ERR_INVALID, "mask must be at least 16x16");
+  if (norm_passes < 0 || norm_passes > 2) return fail(GP_ERR_INVALID, "norm_passes must be 0, 1 or 2");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t slot = (size_t)obj * c.num_templates + tmpl0;
+  const long long rows = (long long)n * GP_NUM_PATCHES;
+  const size_t plane_off = slot * GP_NUM_PATCHES * GP_AE_DIM;
+  const long long img_stride = (long long)GP_NUM_PATCHES * GP_AE_DIM;
+  if (feat_layout == GP_LAYOUT_CHANNEL_MAJOR)
+    GP_CUDA(gp::launch_split_descriptors(feat, rows, GP_AE_DIM, GP_NUM_PATCHES, img_stride, 1, GP_NUM_PATCHES, norm_passes,
+                                         h->bank.hi + plane_off, h->bank.lo + plane_off, nullptr, s));
+  else if (feat_layout == GP_LAYOUT_PATCH_MAJOR)
+    GP_CUDA(gp::launch_split_descriptors(feat, rows, GP_AE_DIM, GP_NUM_PATCHES, img_stride, GP_AE_DIM, 1, norm_passes,
+                                         h->bank.hi + plane_off, h->bank.lo + plane_off, nullptr, s));
+  else
+    return fail(GP_ERR_INVALID, "unknown feature layout %d", feat_layout);
+  GP_CUDA(gp::launch_sample_mask16(mask, n, H, W, h->bank.mask16 + slot * GP_NUM_PATCHES, s));
+  g_launches += 2;
+  if (ist_feat) {
+    GP_CUDA(gp::launch_transpose_cp(ist_feat, n, GP_IST_DIM, h->bank.ist + slot * GP_NUM_PATCHES * GP_IST_DIM, s));
+    g_launches += 1;
+  }
+  return GP_OK;
+}
+
+int gp_bank_set_poses(gp_handle_t h, const float* K, const float* M, const float* poses, void* stream) {
+  if (!h || !K || !M || !poses) return fail(GP_ERR_INVALID, "null argument");
+  const gp_config_t& c = h->cfg;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t OTg = (size_t)c.num_objects * c.num_templates_global;
+  GP_CUDA(cudaMemcpyAsync(h->bank.K, K, (size_t)c.num_objects * 9 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  GP_CUDA(cudaMemcpyAsync(h->bank.M, M, OTg * 9 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  GP_CUDA(cudaMemcpyAsync(h->bank.pose, poses, OTg * 16 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return GP_OK;
+}
+
+int gp_set_ist_weights(gp_handle_t h, const float* const w[12], int use_tanh) {
+  if (!h || !w) return fail(GP_ERR_INVALID, "null argument");
+  for (int i = 0; i < 12; ++i)
+    if (!w[i]) return fail(GP_ERR_INVALID, "IST weight pointer %d is null", i);
+  gp::IstMlpWeights& m = h->mlp;
+  m.s_w1 = w[0]; m.s_b1 = w[1]; m.s_w2 = w[2]; m.s_b2 = w[3]; m.s_w3 = w[4]; m.s_b3 = w[5];
+  m.i_w1 = w[6]; m.i_b1 = w[7]; m.i_w2 = w[8]; m.i_b2 = w[9]; m.i_w3 = w[10]; m.i_b3 = w[11];
+  m.use_tanh = use_tanh;
+  h->mlp_set = true;
+  return GP_OK;
+}
+
+int gp_set_queries(gp_handle_t h, int B, const float* q_feat, int feat_layout, int norm_passes, const float* q_mask,
+                   int H, int W, const int32_t* q_obj, void* stream) {
+  if (!h || !q_feat || !q_mask || !q_obj) return fail(GP_ERR_INVALID, "null argument");
+  if (B < 1 || B > h->cfg.max_batch) return fail(GP_ERR_INVALID, "batch %d outside [1, max_batch=%d]", B, h->cfg.max_batch);
+  if (H < 16 || W < 16) return fail(GP_ERR_INVALID, "mask must be at least 16x16");
+  if (norm_passes < 0 || norm_passes > 2) return fail(GP_ERR_INVALID, "norm_passes must be 0, 1 or 2");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long rows = (long long)B * GP_NUM_PATCHES;
+  const long long img_stride = (long long)GP_NUM_PATCHES * GP_AE_DIM;
+  if (feat_layout == GP_LAYOUT_CHANNEL_MAJOR)
+    GP_CUDA(gp::launch_split_descriptors(q_feat, rows, GP_AE_DIM, GP_NUM_PATCHES, img_stride, 1, GP_NUM_PATCHES, norm_passes,
+                                         h->ws.q_hi, h->ws.q_lo, nullptr, s));
+  else if (feat_layout == GP_LAYOUT_PATCH_MAJOR)
+    GP_CUDA(gp::launch_split_descriptors(q_feat, rows, GP_AE_DIM, GP_NUM_PATCHES, img_stride, GP_AE_DIM, 1, norm_passes,
+                                         h->ws.q_hi, h->ws.q_lo, nullptr, s));
+  else
+    return fail(GP_ERR_INVALID, "unknown feature layout %d", feat_layout);
+  GP_CUDA(gp::launch_sample_mask16(q_mask, B, H, W, h->ws.q_mask16, s));
+  GP_CUDA(cudaMemcpyAsync(h->ws.q_obj, q_obj, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  GP_CUDA(gp::launch_object_order(h->ws.q_obj, B, h->cfg.num_objects, h->ws.perm, s));
+  g_launches += 3;
+  h->cur_B = B;
+  return GP_OK;
+}
+
+static int run_sim(gp_context* h, int B, cudaStream_t s, float* debug_tile = nullptr) {
+  gp::SimSearchParams p;
+  p.num_items = B * h->cfg.num_templates;
+  p.B = B;
+  p.T = h->cfg.num_templates;
+  p.perm = h->ws.perm;
+  p.q_obj = h->ws.q_obj;
+  p.q_mask = h->ws.q_mask16;
+  p.bank_mask = h->bank.mask16;
+  p.sim_threshold = h->cfg.sim_threshold;
+  p.patch_threshold = h->cfg.patch_threshold;
+  p.passes = h->cfg.precision == GP_PRECISION_FP32_SPLIT ? 3 : 1;
+  p.sim_avg = h->ws.sim_avg;
+  p.rec_score = h->ws.rec_score;
+  p.rec_idx = h->ws.rec_idx;
+  p.rec_valid = h->ws.rec_valid;
+  p.debug_tile = debug_tile;
+  GP_CUDA(gp::launch_sim_search(h->tm_q_hi, h->tm_q_lo, h->tm_t_hi, h->tm_t_lo, p, h->num_sms, s));
+  g_launches += 1;
+  return GP_OK;
+}
+
+int gp_sim_candidates(gp_handle_t h, int B, const gp_candidates_t* out, void* stream) {
+  if (!h || !out) return fail(GP_ERR_INVALID, "null argument");
+  if (B != h->cur_B) return fail(GP_ERR_STATE, "gp_set_queries staged %d queries, search asked for %d", h->cur_B, B);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int e = run_sim(h, B, s)) return e;
+  gp::TopkSelectParams t;
+  t.B = B; t.T = h->cfg.num_templates; t.k = h->cfg.top_k;
+  t.id_stride = h->cfg.template_id_stride; t.id_offset = h->cfg.template_id_offset;
+  t.sim_avg = h->ws.sim_avg; t.rec_score = h->ws.rec_score; t.rec_idx = h->ws.rec_idx; t.rec_valid = h->ws.rec_valid;
+  t.cand_score = out->score; t.cand_id = out->id; t.cand_pts_score = out->pts_score; t.cand_idx = out->idx;
+  t.cand_valid = out->valid;
+  GP_CUDA(gp::launch_topk_select(t, s));
+  g_launches += 1;
+  return GP_OK;
+}
+
+int gp_topk_merge(gp_handle_t h, int B, int G, const gp_candidates_t* g, const gp_matches_t* out, void* stream) {
+  if (!h || !g || !out) return fail(GP_ERR_INVALID, "null argument");
+  if (B < 1 || G < 1 || G * h->cfg.top_k > 64) return fail(GP_ERR_INVALID, "B=%d G=%d: need G*k <= 64", B, G);
+  gp::TopkMergeParams m;
+  m.B = B; m.k = h->cfg.top_k; m.G = G;
+  m.cand_score = g->score; m.cand_id = g->id; m.cand_pts_score = g->pts_score; m.cand_idx = g->idx; m.cand_valid = g->valid;
+  m.id_src = reinterpret_cast<long long*>(out->id_src); m.score_src = out->score_src; m.score_pts = out->score_pts;
+  m.tar_pts = reinterpret_cast<long long*>(out->tar_pts); m.src_pts = reinterpret_cast<long long*>(out->src_pts);
+  GP_CUDA(gp::launch_topk_merge_expand(m, static_cast<cudaStream_t>(stream)));
+  g_launches += 1;
+  return GP_OK;
+}
+
+int gp_sim_topk(gp_handle_t h, int B, const gp_matches_t* out, void* stream) {
+  if (!h || !out) return fail(GP_ERR_INVALID, "null argument");
+  gp_candidates_t c;
+  c.score = h->ws.c_score; c.id = h->ws.c_id; c.pts_score = h->ws.c_pts_score; c.idx = h->ws.c_idx; c.valid = h->ws.c_valid;
+  if (int e = gp_sim_candidates(h, B, &c, stream)) return e;
+  return gp_topk_merge(h, B, 1, &c, out, stream);
+}
+
+int gp_ist_mlp(gp_handle_t h, int B, const float* q_ist, const gp_matches_t* m, float* rel_scale, float* rel_inplane,
+               void* stream) {
+  if (!h || !q_ist || !m || !rel_scale || !rel_inplane) return fail(GP_ERR_INVALID, "null argument");
+  if (!h->mlp_set) return fail(GP_ERR_STATE, "gp_set_ist_weights has not been called");
+  if (B != h->cur_B) return fail(GP_ERR_STATE, "gp_set_queries staged %d queries, gp_ist_mlp asked for %d", h->cur_B, B);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GP_CUDA(gp::launch_transpose_cp(q_ist, B, GP_IST_DIM, h->ws.q_ist, s));
+  gp::IstMlpParams p;
+  p.B = B; p.k = h->cfg.top_k; p.T = h->cfg.num_templates;
+  p.id_stride = h->cfg.template_id_stride; p.id_offset = h->cfg.template_id_offset;
+  p.id_src = reinterpret_cast<const long long*>(m->id_src);
+  p.src_pts = reinterpret_cast<const long long*>(m->src_pts);
+  p.tar_pts = reinterpret_cast<const long long*>(m->tar_pts);
+  p.q_obj = h->ws.q_obj; p.q_ist = h->ws.q_ist; p.bank_ist = h->bank.ist;
+  p.rel_scale = rel_scale; p.rel_inplane = rel_inplane;
+  p.row_count = h->ws.row_count; p.row_ids = h->ws.row_ids; p.hidden1 = h->ws.hidden1; p.hidden2 = h->ws.hidden2;
+  GP_CUDA(gp::launch_ist_mlp(h->mlp, p, s));
+  g_launches += 5;
+  return GP_OK;
+}
+
+int gp_ransac(gp_handle_t h, int B, const gp_matches_t* m, const float* rel_scale, const float* rel_inplane,
+              const gp_ransac_out_t* out, void* stream) {
+  if (!h || !m || !rel_scale || !rel_inplane || !out || !out->inlier_count) return fail(GP_ERR_INVALID, "null argument");
+  if (B < 1) return fail(GP_ERR_INVALID, "B must be >= 1");
+  gp::RansacParams p;
+  p.B = B; p.k = h->cfg.top_k; p.pixel_threshold = h->cfg.pixel_threshold; p.patch_size = h->cfg.patch_size;
+  p.src_pts = reinterpret_cast<const long long*>(m->src_pts);
+  p.tar_pts = reinterpret_cast<const long long*>(m->tar_pts);
+  p.rel_scale = rel_scale; p.rel_inplane = rel_inplane;
+  p.M = out->M; p.failed = out->failed;
+  p.in_src = reinterpret_cast<long long*>(out->inlier_src_pts);
+  p.in_tar = reinterpret_cast<long long*>(out->inlier_tar_pts);
+  p.in_score = reinterpret_cast<long long*>(out->inlier_scores);
+  p.in_count = out->inlier_count;
+  GP_CUDA(gp::launch_ransac(p, static_cast<cudaStream_t>(stream)));
+  g_launches += 1;
+  return GP_OK;
+}
+
+int gp_sort_and_pose(gp_handle_t h, int B, const float* q_K, const float* q_M, const gp_matches_t* m,
+                     const float* rel_scale, const float* rel_inplane, const gp_ransac_out_t* r,
+                     const gp_predictions_t* o, void* stream) {
+  if (!h || !q_K || !q_M || !m || !rel_scale || !rel_inplane || !r || !o) return fail(GP_ERR_INVALID, "null argument");
+  if (B != h->cur_B) return fail(GP_ERR_STATE, "gp_set_queries staged %d queries, gp_sort_and_pose asked for %d", h->cur_B, B);
+  gp::PoseParams p;
+  p.B = B; p.k = h->cfg.top_k; p.T = h->cfg.num_templates_global;
+  p.q_obj = h->ws.q_obj; p.q_K = q_K; p.q_M = q_M;
+  p.tmpl_K = h->bank.K; p.tmpl_M = h->bank.M; p.tmpl_pose = h->bank.pose;
+  p.in_count = r->inlier_count;
+  p.id_src = reinterpret_cast<const long long*>(m->id_src); p.score_src = m->score_src; p.score_pts = m->score_pts;
+  p.tar_pts = reinterpret_cast<const long long*>(m->tar_pts); p.src_pts = reinterpret_cast<const long long*>(m->src_pts);
+  p.rel_scale = rel_scale; p.rel_inplane = rel_inplane;
+  p.M = r->M; p.failed = r->failed;
+  p.in_src = reinterpret_cast<const long long*>(r->inlier_src_pts);
+  p.in_tar = reinterpret_cast<const long long*>(r->inlier_tar_pts);
+  p.in_score = reinterpret_cast<const long long*>(r->inlier_scores);
+  p.o_id_src = reinterpret_cast<long long*>(o->matches.id_src); p.o_score_src = o->matches.score_src;
+  p.o_score_pts = o->matches.score_pts;
+  p.o_tar_pts = reinterpret_cast<long long*>(o->matches.tar_pts); p.o_src_pts = reinterpret_cast<long long*>(o->matches.src_pts);
+  p.o_rel_scale = o->rel_scale; p.o_rel_inplane = o->rel_inplane;
+  p.o_M = o->ransac.M; p.o_failed = o->ransac.failed;
+  p.o_in_src = reinterpret_cast<long long*>(o->ransac.inlier_src_pts);
+  p.o_in_tar = reinterpret_cast<long long*>(o->ransac.inlier_tar_pts);
+  p.o_in_score = reinterpret_cast<long long*>(o->ransac.inlier_scores);
+  p.o_scores = o->scores; p.o_poses = o->poses;
+  GP_CUDA(gp::launch_sort_and_pose(p, static_cast<cudaStream_t>(stream)));
+  g_launches += 1;
+  return GP_OK;
+}
+
+int gp_debug_sim_tiles(gp_handle_t h, int B, float* tiles, void* stream) {
+  if (!h || !tiles) return fail(GP_ERR_INVALID, "null argument");
+  if (B != h->cur_B) return fail(GP_ERR_STATE, "gp_set_queries staged %d queries, debug asked for %d", h->cur_B, B);
+  return run_sim(h, B, static_cast<cudaStream_t>(stream), tiles);
+}
+
+int gp_time_sim_kernel(gp_handle_t h, int B, int iters, float* avg_ms, void* stream) {
+  if (!h || !avg_ms || iters < 1) return fail(GP_ERR_INVALID, "bad argument");
+  if (B != h->cur_B) return fail(GP_ERR_STATE, "gp_set_queries staged %d queries, timing asked for %d", h->cur_B, B);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaEvent_t e0, e1;
+  GP_CUDA(cudaEventCreate(&e0));
+  GP_CUDA(cudaEventCreate(&e1));
+  if (int e = run_sim(h, B, s)) return e;   // warm-up
+  GP_CUDA(cudaEventRecord(e0, s));
+  for (int i = 0; i < iters; ++i)
+    if (int e = run_sim(h, B, s)) return e;
+  GP_CUDA(cudaEventRecord(e1, s));
+  GP_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  GP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *avg_ms = ms / iters;
+  return GP_OK;
+}
+
+}  // extern "C"

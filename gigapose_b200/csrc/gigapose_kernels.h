@@ -1,0 +1,146 @@
+// Internal kernel-launch interface shared by the .cu files and the C-ABI layer (api.cu).  Not installed.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+
+namespace gp {
+
+// ---------------------------------------------------------------- similarity search (sim_search.cu)
+struct SimSearchParams {
+  int num_items;              // B * T
+  int B;                      // queries in this call
+  int T;                      // templates per object held by this rank
+  const int* perm;            // [B] query order (queries of one object adjacent -> template tiles shared through L2)
+  const int* q_obj;           // [B] 0-based object index of every query
+  const float* q_mask;        // [B,256]  query mask sampled at the 16x16 patch grid
+  const float* bank_mask;     // [O*T,256]
+  float sim_threshold;
+  float patch_threshold;
+  int passes;                 // 3 = hi*hi + hi*lo + lo*hi (fp32-faithful), 1 = hi*hi only (plain bf16)
+  float* sim_avg;             // [B,T]      per-template score (matching.py:274-278)
+  float* rec_score;           // [B,T,256]  score_tar2src
+  uint8_t* rec_idx;           // [B,T,256]  idx_tar2src
+  uint8_t* rec_valid;         // [B,T,256]  mask_all != 0
+  float* debug_tile;          // nullable [num_items,256,256]: raw fp32 similarity tiles (tests only)
+};
+cudaError_t launch_sim_search(const CUtensorMap& q_hi, const CUtensorMap& q_lo, const CUtensorMap& t_hi,
+                              const CUtensorMap& t_lo, const SimSearchParams& p, int num_sms, cudaStream_t stream);
+int sim_search_smem_bytes();
+
+struct TopkSelectParams {
+  int B, T, k;
+  int id_stride, id_offset;   // global template id = local * id_stride + id_offset (template-interleaved shards)
+  const float* sim_avg;
+  const float* rec_score;
+  const uint8_t* rec_idx;
+  const uint8_t* rec_valid;
+  float* cand_score;          // [B,k]
+  int* cand_id;               // [B,k]
+  float* cand_pts_score;      // [B,k,256]
+  uint8_t* cand_idx;          // [B,k,256]
+  uint8_t* cand_valid;        // [B,k,256]
+};
+cudaError_t launch_topk_select(const TopkSelectParams& p, cudaStream_t stream);
+
+struct TopkMergeParams {
+  int B, k, G;                // G candidate lists laid out [G][B][k]
+  const float* cand_score;
+  const int* cand_id;
+  const float* cand_pts_score;
+  const uint8_t* cand_idx;
+  const uint8_t* cand_valid;
+  long long* id_src;          // [B,k]
+  float* score_src;           // [B,k]
+  float* score_pts;           // [B,k,256]
+  long long* tar_pts;         // [B,k,256,2]
+  long long* src_pts;         // [B,k,256,2]
+};
+cudaError_t launch_topk_merge_expand(const TopkMergeParams& p, cudaStream_t stream);
+
+// ---------------------------------------------------------------- descriptor / mask preparation (prep.cu)
+// x: n_rows descriptors of `C` channels; element (row r, channel c) at x[(r / rows_per_img) * img_stride +
+// (r % rows_per_img) * row_stride + c * chan_stride].  L2-normalises each row `norm_passes` times
+// (F.normalize semantics, eps 1e-12) and writes the bf16 hi / lo planes [n_rows, C].
+cudaError_t launch_split_descriptors(const float* x, long long n_rows, int C, int rows_per_img, long long img_stride,
+                                     long long row_stride, long long chan_stride, int norm_passes,
+                                     uint16_t* hi, uint16_t* lo, float* normalized_out /*nullable [n_rows,C]*/,
+                                     cudaStream_t stream);
+// nearest-neighbour H x W -> 16 x 16 sampling of float masks (F.interpolate default mode), [n,H,W] -> [n,256]
+cudaError_t launch_sample_mask16(const float* mask, long long n, int H, int W, float* out, cudaStream_t stream);
+// perm[B] = stable order of the queries by object id, so that tiles sharing a template run back to back
+cudaError_t launch_object_order(const int* q_obj, int B, int num_objects, int* perm, cudaStream_t stream);
+// [n, C, 256] (channel-major, reference layout) -> [n, 256, C] (patch-major)
+cudaError_t launch_transpose_cp(const float* in, long long n, int C, float* out, cudaStream_t stream);
+
+// ---------------------------------------------------------------- IST per-correspondence MLP (ist_mlp.cu)
+struct IstMlpWeights {        // fp32, row-major [out,in] exactly as nn.Linear stores them (ist_net.py:140-155)
+  const float *s_w1, *s_b1, *s_w2, *s_b2, *s_w3, *s_b3;   // scale head   512->512->256->1
+  const float *i_w1, *i_b1, *i_w2, *i_b2, *i_w3, *i_b3;   // inplane head 512->512->256->2 (+tanh)
+  int use_tanh;
+};
+struct IstMlpParams {
+  int B, k;
+  int T;                      // templates per object held locally (bank row = (obj*T + local_id))
+  int id_stride, id_offset;   // local id = (global id - id_offset) / id_stride
+  const long long* id_src;    // [B,k] global template ids
+  const long long* src_pts;   // [B,k,256,2]
+  const long long* tar_pts;   // [B,k,256,2]
+  const int* q_obj;           // [B]
+  const float* q_ist;         // [B,256(patch),256(ch)]   patch-major query IST features
+  const float* bank_ist;      // [O*T,256(patch),256(ch)] patch-major template IST features
+  float* rel_scale;           // [B,k,256]   (-1000 where invalid, ist_net.py:110-113)
+  float* rel_inplane;         // [B,k,256,2]
+  // workspace
+  int* row_count;             // [1]
+  int* row_ids;               // [B*k*256] flat (b,k,t) of valid rows
+  float* hidden1;             // [B*k*256, 1024]
+  float* hidden2;             // [B*k*256, 512]
+};
+cudaError_t launch_ist_mlp(const IstMlpWeights& w, const IstMlpParams& p, cudaStream_t stream);
+
+// ---------------------------------------------------------------- RANSAC + scoring + pose lifting (ransac_pose.cu)
+struct RansacParams {
+  int B, k;
+  float pixel_threshold;      // 14 px (poses.py:18)
+  int patch_size;             // 14
+  const long long* src_pts;   // [B,k,256,2]
+  const long long* tar_pts;
+  const float* rel_scale;     // [B,k,256]
+  const float* rel_inplane;   // [B,k,256,2]
+  float* M;                   // [B,k,3,3]
+  uint8_t* failed;            // [B,k]
+  long long* in_src;          // [B,k,256,2]
+  long long* in_tar;          // [B,k,256,2]
+  long long* in_score;        // [B,k,256]
+  int* in_count;              // [B,k]
+};
+cudaError_t launch_ransac(const RansacParams& p, cudaStream_t stream);
+
+struct PoseParams {
+  int B, k, T;                // T = GLOBAL templates per object in the pose tables
+  const int* q_obj;           // [B]
+  const float* q_K;           // [B,3,3]
+  const float* q_M;           // [B,3,3]
+  const float* tmpl_K;        // [O,3,3]
+  const float* tmpl_M;        // [O,T,3,3]
+  const float* tmpl_pose;     // [O,T,4,4]
+  // unsorted inputs (per (b,k))
+  const int* in_count;        // [B,k] inlier counts
+  const long long* id_src; const float* score_src; const float* score_pts;
+  const long long* tar_pts; const long long* src_pts;
+  const float* rel_scale; const float* rel_inplane;
+  const float* M; const uint8_t* failed;
+  const long long* in_src; const long long* in_tar; const long long* in_score;
+  // sorted outputs (gigaPose.py:588-604)
+  long long* o_id_src; float* o_score_src; float* o_score_pts;
+  long long* o_tar_pts; long long* o_src_pts;
+  float* o_rel_scale; float* o_rel_inplane;
+  float* o_M; uint8_t* o_failed;
+  long long* o_in_src; long long* o_in_tar; long long* o_in_score;
+  float* o_scores;            // [B,k]
+  float* o_poses;             // [B,k,4,4]
+};
+cudaError_t launch_sort_and_pose(const PoseParams& p, cudaStream_t stream);
+
+}  // namespace gp

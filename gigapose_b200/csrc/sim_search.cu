@@ -1,0 +1,404 @@
+// Fused query<->template patch-similarity search for sm_100a (row a4 of SURVEY.md §8; replaces
+// LocalSimilarity.test, reference src/models/matching.py:188-316 with helpers :63-113).
+//
+// One work item = one (query b, template n) pair = one 256(t) x 256(s) x 1024(c) similarity tile.
+// A persistent CTA per SM walks the item list:
+//   warp 0   : TMA producer  -- streams K-blocks of the query / template descriptor planes into a 3-stage smem ring
+//   warp 1   : UMMA issuer   -- tcgen05.mma (cta_group::1, M=128, N=256, K=16, bf16 -> fp32) into TMEM;
+//                               the two t-halves of the tile live in TMEM columns [0,256) and [256,512)
+//   warp 2   : TMEM allocator
+//   warps 4-11: epilogue     -- tcgen05.ld the fp32 tile, apply masks + threshold (matching.py:234-236), row
+//                               max/arg-max (t->s) in registers, column max/arg-max (s->t) with redux.sync +
+//                               ballot, cycle-consistency / validity masks (matching.py:80-113,247-271) and the
+//                               per-template score (matching.py:274-278).  The [B,N,256,256] similarity tensor
+//                               never reaches HBM; per item only a 1.5 KB record + one float are written.
+//
+// Precision: descriptors are stored as two bf16 planes (hi = bf16(x), lo = bf16(x - hi)); the tile is accumulated
+// as hi*hi + hi*lo + lo*hi in fp32 (3 tensor-core passes, ~2^-17 relative operand error), so the thresholded /
+// arg-max'ed results agree with the reference's fp32 einsum up to fp32 accumulation-order noise.  `passes = 1`
+// runs hi*hi only (plain bf16 tensor-core similarity, 3x less tensor work, not index-exact).
+#include "gigapose_kernels.h"
+#include "common.cuh"
+#include <cstdio>
+
+namespace gp {
+
+namespace {
+
+constexpr int kP = 256;                         // patches per crop (16 x 16)
+constexpr int kC = 1024;                        // descriptor channels
+constexpr int kBlockK = 32;                     // bf16 elements per stage row: 64 B = SWIZZLE_64B span
+constexpr int kRowBytes = kBlockK * 2;
+constexpr int kStages = 3;
+constexpr int kPlaneBytes = kP * kRowBytes;     // 16 KB: 256 rows x 64 B
+constexpr int kStageBytes = 4 * kPlaneBytes;    // q_hi, q_lo, t_hi, t_lo
+constexpr int kNumKBlocks = kC / kBlockK;       // 32
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;     // 256 == kP: epilogue thread i owns query patch t = i
+constexpr int kThreads = 4 * 32 + kEpiThreads;  // 384
+constexpr int kTmemCols = 512;
+constexpr uint32_t kIdesc = umma_idesc_f16(128, 256, /*bf16*/ 1);
+
+struct __align__(8) SimSmemTail {
+  float smask[kP];                              // template mask sampled at 16x16 (float: alpha masks are not binary)
+  float tmask[kP];                              // query mask sampled at 16x16
+  float pmax[kEpiWarps][kP];                    // per-epilogue-warp partial column max (32 t-rows each)
+  float cmax[kP];                               // score_src2tar
+  float red[2][kEpiWarps];
+  uint8_t pidx[kEpiWarps][kP];
+  uint8_t cidx[kP];                             // idx_src2tar
+  uint64_t full_bar[kStages];
+  uint64_t empty_bar[kStages];
+  uint64_t tmem_full_bar;
+  uint64_t tmem_empty_bar;
+  uint32_t tmem_base;
+};
+
+constexpr int kSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + sizeof(SimSmemTail);
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1)
+sim_search_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
+                  const __grid_constant__ CUtensorMap tm_t_hi, const __grid_constant__ CUtensorMap tm_t_lo,
+                  SimSearchParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_64B atoms repeat every 512 B; keep every plane 1024 B aligned
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  SimSmemTail& tail = *reinterpret_cast<SimSmemTail*>(smem + kStages * kStageBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int passes = p.passes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&tail.full_bar[s], 1);
+      mbar_init(&tail.empty_bar[s], 1);
+    }
+    mbar_init(&tail.tmem_full_bar, 1);
+    mbar_init(&tail.tmem_empty_bar, kEpiWarps);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q_hi);
+    tma_prefetch_desc(&tm_t_hi);
+    if (passes == 3) {
+      tma_prefetch_desc(&tm_q_lo);
+      tma_prefetch_desc(&tm_t_lo);
+    }
+  }
+  if (warp == 2) tmem_alloc(&tail.tmem_base, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tail.tmem_base;
+
+  if (warp == 0) {
+    // ======================================= TMA producer =======================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = (passes == 3 ? 4 : 2) * kPlaneBytes;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int n = item / p.B;
+        const int b = p.perm[item - n * p.B];
+        const int q_row = b * kP;
+        const int t_row = (p.q_obj[b] * p.T + n) * kP;
+        for (int kb = 0; kb < kNumKBlocks; ++kb) {
+          mbar_wait(&tail.empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * kStageBytes;
+          mbar_arrive_expect_tx(&tail.full_bar[stage], tx_bytes);
+          tma_load_2d(st + 0 * kPlaneBytes, &tm_q_hi, &tail.full_bar[stage], kb * kBlockK, q_row);
+          tma_load_2d(st + 2 * kPlaneBytes, &tm_t_hi, &tail.full_bar[stage], kb * kBlockK, t_row);
+          if (passes == 3) {
+            tma_load_2d(st + 3 * kPlaneBytes, &tm_t_lo, &tail.full_bar[stage], kb * kBlockK, t_row);
+            tma_load_2d(st + 1 * kPlaneBytes, &tm_q_lo, &tail.full_bar[stage], kb * kBlockK, q_row);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================= UMMA issuer ========================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, tphase = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        mbar_wait(&tail.tmem_empty_bar, tphase ^ 1);          // epilogue has drained the previous tile
+        tc_fence_after();
+        for (int kb = 0; kb < kNumKBlocks; ++kb) {
+          mbar_wait(&tail.full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + stage * kStageBytes);
+          const uint32_t q_hi = st, q_lo = st + kPlaneBytes, t_hi = st + 2 * kPlaneBytes, t_lo = st + 3 * kPlaneBytes;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t d = tmem_base + half * 256;
+            const uint32_t aoff = half * (128 * kRowBytes);
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+              if (pass < passes) {
+                const uint32_t a = (pass == 2 ? q_lo : q_hi) + aoff;
+                const uint32_t bsm = (pass == 1 ? t_lo : t_hi);
+#pragma unroll
+                for (int k16 = 0; k16 < kBlockK / 16; ++k16) {
+                  const uint32_t acc = (kb | pass | k16) != 0 ? 1u : 0u;
+                  umma_f16(d, umma_desc_kmajor<kRowBytes>(a + k16 * 32), umma_desc_kmajor<kRowBytes>(bsm + k16 * 32),
+                           kIdesc, acc);
+                }
+              }
+            }
+          }
+          umma_commit(&tail.empty_bar[stage]);                  // frees the smem stage once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tail.tmem_full_bar);                       // accumulators complete -> epilogue
+        tphase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ========================================= epilogue =========================================
+    const int e = warp - 4;                  // 0..7 ; TMEM lane quarter = warp % 4 = e % 4, t-half = e / 4
+    const int t = e * 32 + lane;             // query patch owned by this thread (row of the tile)
+    const uint32_t taddr = tmem_base + ((uint32_t)((e & 3) * 32) << 16) + (uint32_t)((e >> 2) * 256);
+    const float thr = p.sim_threshold;
+    uint32_t tphase = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int n = item / p.B;
+      const int b = p.perm[item - n * p.B];
+      const size_t rec = (size_t)b * p.T + n;
+      tail.smask[t] = p.bank_mask[((size_t)p.q_obj[b] * p.T + n) * kP + t];
+      const float tm = p.q_mask[(size_t)b * kP + t];
+      tail.tmask[t] = tm;
+      named_barrier_sync(1, kEpiThreads);
+
+      mbar_wait(&tail.tmem_full_bar, tphase);
+      tphase ^= 1;
+      tc_fence_after();
+
+      float rmax = -1.0f;                    // all candidates are >= 0 after thresholding -> first max wins
+      int ridx = 0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kP; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c0, r);
+        tmem_ld_wait();
+        uint32_t keep_m = 0, keep_i = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (p.debug_tile) p.debug_tile[((size_t)item * kP + t) * kP + c0 + j] = __uint_as_float(r[j]);
+          float v = __uint_as_float(r[j]) * tail.smask[c0 + j];          // matching.py:234
+          v = v * tm;                                                     // matching.py:235
+          v = (v < thr) ? 0.0f : v;                                       // matching.py:236
+          if (v > rmax) { rmax = v; ridx = c0 + j; }                      // torch.max(dim=3): first maximum
+          const uint32_t bits = __float_as_uint(v);                       // v >= 0: float order == uint order
+          const uint32_t m = __reduce_max_sync(0xffffffffu, bits);
+          const uint32_t bal = __ballot_sync(0xffffffffu, bits == m);
+          if (lane == j) { keep_m = m; keep_i = __ffs(bal) - 1; }         // torch.max(dim=2): first maximum
+        }
+        tail.pmax[e][c0 + lane] = __uint_as_float(keep_m);
+        tail.pidx[e][c0 + lane] = (uint8_t)(e * 32 + keep_i);
+      }
+      // TMEM fully read: hand the accumulators back to the MMA warp before the (smem-only) tail of the epilogue
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail.tmem_empty_bar);
+      named_barrier_sync(1, kEpiThreads);
+
+      {  // combine the 8 partial column maxima in ascending-t order (strict > keeps the first maximum)
+        float best = tail.pmax[0][t];
+        uint8_t bi = tail.pidx[0][t];
+#pragma unroll
+        for (int g = 1; g < kEpiWarps; ++g) {
+          const float v = tail.pmax[g][t];
+          if (v > best) { best = v; bi = tail.pidx[g][t]; }
+        }
+        tail.cmax[t] = best;
+        tail.cidx[t] = bi;
+      }
+      named_barrier_sync(1, kEpiThreads);
+
+      // matching.py:247-271 for query patch t
+      const bool mask_sim = rmax >= thr;
+      const int back = tail.cidx[ridx];                                   // idx_src2tar[idx_tar2src[t]]
+      const float dx = (float)(back & 15) - (float)(t & 15);
+      const float dy = (float)(back >> 4) - (float)(t >> 4);
+      const bool mask_cycle = (sqrtf(dx * dx + dy * dy) <= p.patch_threshold) && (tail.cmax[ridx] >= thr);
+      // reference quirk kept on purpose: `idx_src2tar != 0` is indexed by s but multiplied position-wise with t
+      float mnz = tm * tail.smask[ridx];
+      mnz = mnz * (tail.cidx[t] != 0 ? 1.0f : 0.0f);
+      mnz = mnz * (ridx != 0 ? 1.0f : 0.0f);
+      const float mall = (mask_sim && mask_cycle) ? mnz : 0.0f;
+      float s_contrib = rmax * mall, s_mall = mall;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        s_contrib += __shfl_xor_sync(0xffffffffu, s_contrib, off);
+        s_mall += __shfl_xor_sync(0xffffffffu, s_mall, off);
+      }
+      if (lane == 0) { tail.red[0][e] = s_contrib; tail.red[1][e] = s_mall; }
+      p.rec_score[rec * kP + t] = rmax;
+      p.rec_idx[rec * kP + t] = (uint8_t)ridx;
+      p.rec_valid[rec * kP + t] = (mall != 0.0f) ? 1 : 0;
+      named_barrier_sync(1, kEpiThreads);
+      if (t == 0) {
+        float a = 0.f, m = 0.f;
+#pragma unroll
+        for (int g = 0; g < kEpiWarps; ++g) { a += tail.red[0][g]; m += tail.red[1][g]; }
+        p.sim_avg[rec] = (m > 0.f) ? a / (float)kP : 0.0f;              // matching.py:274-278
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// top-k template selection (matching.py:279) + compact candidate records
+// ------------------------------------------------------------------------------------------------------------
+// One CTA per query.  k rounds of block-wide arg-max over the per-template scores; ties break towards the lowest
+// template index (torch.topk leaves tie order unspecified).  Emits one compact record per winner:
+//   cand_score[b,k] f32, cand_id[b,k] i32 (GLOBAL template id = local * id_stride + id_offset),
+//   cand_pts_score[b,k,256] f32, cand_idx[b,k,256] u8, cand_valid[b,k,256] u8
+__global__ void __launch_bounds__(256)
+topk_select_kernel(TopkSelectParams p) {
+  extern __shared__ float s_val[];                 // [T]
+  __shared__ float s_wv[8];
+  __shared__ int s_wi[8];
+  __shared__ int s_win;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < p.T; i += 256) s_val[i] = p.sim_avg[(size_t)b * p.T + i];
+  __syncthreads();
+  for (int kk = 0; kk < p.k; ++kk) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < p.T; i += 256) {
+      const float v = s_val[i];
+      if (v != -INFINITY && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { s_wv[warp] = bv; s_wi[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (s_wv[w] > bv || (s_wv[w] == bv && s_wi[w] < bi)) { bv = s_wv[w]; bi = s_wi[w]; }
+      s_win = bi;
+      const size_t o = (size_t)b * p.k + kk;
+      if (bi < p.T) {
+        p.cand_score[o] = bv;
+        p.cand_id[o] = bi * p.id_stride + p.id_offset;
+        s_val[bi] = -INFINITY;                     // exclude from later rounds (scores themselves are >= 0)
+      } else {                                     // fewer than k local templates: padding candidate
+        p.cand_score[o] = -INFINITY;
+        p.cand_id[o] = 0x7fffffff;
+      }
+    }
+    __syncthreads();
+    const int win = s_win;
+    const size_t o = ((size_t)b * p.k + kk) * kP + tid;
+    if (win < p.T) {
+      const size_t r = ((size_t)b * p.T + win) * kP + tid;
+      p.cand_pts_score[o] = p.rec_score[r];
+      p.cand_idx[o] = p.rec_idx[r];
+      p.cand_valid[o] = p.rec_valid[r];
+    } else {
+      p.cand_pts_score[o] = 0.f;
+      p.cand_idx[o] = 0;
+      p.cand_valid[o] = 0;
+    }
+    __syncthreads();
+  }
+}
+
+// Merge G per-shard candidate lists (G = 1 on a single GPU) into the global top-k and expand the winners into the
+// reference's output format (matching.py:282-316, format_prediction :29-61):
+//   id_src[B,k] i64, score_src[B,k] f32, score_pts[B,k,256] f32, tar_pts/src_pts[B,k,256,2] i64 (-1 = invalid).
+// Candidates are laid out [G][B][k]; ordering = score descending, then global template id ascending.
+__global__ void __launch_bounds__(256)
+topk_merge_expand_kernel(TopkMergeParams p) {
+  __shared__ int s_sel[32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int ncand = p.G * p.k;
+  if (tid == 0) {
+    // tiny selection sort over <= 8*k candidates
+    unsigned long long used = 0;   // supports ncand <= 64
+    for (int kk = 0; kk < p.k; ++kk) {
+      float bv = 0.f; int bid = 0; int bc = -1;
+      for (int c = 0; c < ncand; ++c) {
+        if (used >> c & 1ull) continue;
+        const int g = c / p.k, j = c - g * p.k;
+        const size_t o = ((size_t)g * p.B + b) * p.k + j;
+        const float v = p.cand_score[o];
+        const int id = p.cand_id[o];
+        if (bc < 0 || v > bv || (v == bv && id < bid)) { bv = v; bid = id; bc = c; }
+      }
+      used |= 1ull << bc;
+      s_sel[kk] = bc;
+    }
+  }
+  __syncthreads();
+  for (int kk = 0; kk < p.k; ++kk) {
+    const int c = s_sel[kk];
+    const int g = c / p.k, j = c - g * p.k;
+    const size_t o = ((size_t)g * p.B + b) * p.k + j;
+    const size_t dst = (size_t)b * p.k + kk;
+    if (tid == 0) {
+      p.id_src[dst] = (long long)p.cand_id[o];
+      p.score_src[dst] = p.cand_score[o];
+    }
+    const int t = tid;
+    const bool valid = p.cand_valid[o * kP + t] != 0;
+    const int s = p.cand_idx[o * kP + t];
+    p.score_pts[dst * kP + t] = p.cand_pts_score[o * kP + t];
+    longlong2 tp, sp;
+    tp.x = valid ? (long long)(t & 15) : -1ll;
+    tp.y = valid ? (long long)(t >> 4) : -1ll;
+    sp.x = valid ? (long long)(s & 15) : -1ll;
+    sp.y = valid ? (long long)(s >> 4) : -1ll;
+    reinterpret_cast<longlong2*>(p.tar_pts)[dst * kP + t] = tp;
+    reinterpret_cast<longlong2*>(p.src_pts)[dst * kP + t] = sp;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------------------
+cudaError_t launch_sim_search(const CUtensorMap& q_hi, const CUtensorMap& q_lo, const CUtensorMap& t_hi,
+                              const CUtensorMap& t_lo, const SimSearchParams& p, int num_sms, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(sim_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (p.num_items <= 0) return cudaSuccess;
+  const int grid = p.num_items < num_sms ? p.num_items : num_sms;
+  sim_search_kernel<<<grid, kThreads, kSmemBytes, stream>>>(q_hi, q_lo, t_hi, t_lo, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_topk_select(const TopkSelectParams& p, cudaStream_t stream) {
+  if (p.B <= 0) return cudaSuccess;
+  topk_select_kernel<<<p.B, 256, p.T * sizeof(float), stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_topk_merge_expand(const TopkMergeParams& p, cudaStream_t stream) {
+  if (p.B <= 0) return cudaSuccess;
+  topk_merge_expand_kernel<<<p.B, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+int sim_search_smem_bytes() { return kSmemBytes; }
+
+}  // namespace gp

@@ -1,0 +1,263 @@
+"""Host-side handle over the C ABI: owns the template bank + workspace as torch-allocated HBM and launches the
+sm_100a kernels on torch's current stream.  PyTorch is used for device memory, streams and torch.distributed only;
+every arithmetic step below is a kernel of libgigapose_b200.so (no torch fallback)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import (GpCandidates, GpConfig, GpMatches, GpPredictions, GpRansacOut, LAYOUT_CHANNEL_MAJOR,
+                   LAYOUT_PATCH_MAJOR, PRECISION_BF16, PRECISION_FP32_SPLIT, check)
+
+P = 256
+C_AE = 1024
+C_IST = 256
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t: torch.Tensor, device) -> torch.Tensor:
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t
+
+
+def _feature_layout(feat: torch.Tensor):
+    """Accepts [n,C,16,16] (reference layout) or [n,256,C] (patch-major).  A channels-last *view* of a patch-major
+    buffer (what AENet returns) is recognised and used in place, without a copy."""
+    if feat.dim() == 4:
+        n, c, h, w = feat.shape
+        assert h * w == P, f"expected a 16x16 patch grid, got {h}x{w}"
+        if feat.stride() == (P * c, 1, w * c, c):          # [n,16,16,C] memory viewed as [n,C,16,16]
+            return feat, LAYOUT_PATCH_MAJOR
+        return feat.contiguous(), LAYOUT_CHANNEL_MAJOR
+    assert feat.dim() == 3 and feat.shape[1] == P, f"bad descriptor shape {tuple(feat.shape)}"
+    return feat.contiguous(), LAYOUT_PATCH_MAJOR
+
+
+class Engine:
+    """One template bank (or one shard of it) resident on one B200 plus the per-batch workspace."""
+
+    def __init__(self, num_objects: int, num_templates: int, max_batch: int, device="cuda:0", k: int = 5,
+                 sim_threshold: float = 0.5, patch_threshold: float = 3, pixel_threshold: float = 14.0,
+                 patch_size: int = 14, precision: str = "fp32_split", shard_rank: int = 0, shard_world: int = 1,
+                 num_templates_global: Optional[int] = None):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.GigaPoseNativeError("gigapose_b200 runs on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.k = int(k)
+        self.O, self.T, self.max_batch = int(num_objects), int(num_templates), int(max_batch)
+        self.T_global = int(num_templates_global if num_templates_global is not None else num_templates)
+        self.shard_rank, self.shard_world = int(shard_rank), int(shard_world)
+        cfg = GpConfig(abi_version=_lib.GP_ABI_VERSION, device=self.device.index, num_objects=self.O,
+                       num_templates=self.T, num_templates_global=self.T_global,
+                       template_id_stride=self.shard_world, template_id_offset=self.shard_rank,
+                       max_batch=self.max_batch, top_k=self.k, sim_threshold=float(sim_threshold),
+                       patch_threshold=float(patch_threshold), pixel_threshold=float(pixel_threshold),
+                       patch_size=int(patch_size),
+                       precision={"fp32_split": PRECISION_FP32_SPLIT, "bf16": PRECISION_BF16}[precision])
+        self.cfg = cfg
+        self.precision = precision
+        bank_b, ws_b = C.c_size_t(), C.c_size_t()
+        check(self.lib.gp_query_sizes(C.byref(cfg), C.byref(bank_b), C.byref(ws_b)))
+        self.bank_bytes, self.workspace_bytes = bank_b.value, ws_b.value
+        with torch.cuda.device(self.device):
+            # +1 KiB so the carved base can be aligned to 1024 B whatever the allocator returns
+            self._bank_mem = torch.empty(self.bank_bytes + 1024, dtype=torch.uint8, device=self.device)
+            self._ws_mem = torch.empty(self.workspace_bytes + 1024, dtype=torch.uint8, device=self.device)
+            self._bank_mem.zero_()
+        al = lambda t: (t.data_ptr() + 1023) // 1024 * 1024
+        h = C.c_void_p()
+        check(self.lib.gp_create(C.byref(cfg), al(self._bank_mem), al(self._ws_mem), C.byref(h)))
+        self._h = h
+        self._keep = []          # tensors whose device pointers the library retains
+        self._B = 0
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self.lib.gp_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ------------------------------------------------------------------------------------------------ helpers
+    @property
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    # ---------------------------------------------------------------------------------------------- onboarding
+    def bank_write(self, obj: int, tmpl0: int, feat: torch.Tensor, mask: torch.Tensor,
+                   ist_feat: Optional[torch.Tensor] = None, norm_passes: int = 1) -> None:
+        """feat: [n,1024,16,16] or [n,256,1024]; mask: [n,H,W]; ist_feat: [n,256,16,16] (optional)."""
+        feat, layout = _feature_layout(_f32(feat, self.device))
+        mask = _f32(mask, self.device).contiguous()
+        n = feat.shape[0]
+        assert mask.shape[0] == n and mask.dim() == 3
+        if ist_feat is not None:
+            ist_feat = _f32(ist_feat, self.device).contiguous()
+            assert ist_feat.shape == (n, C_IST, 16, 16), tuple(ist_feat.shape)
+        check(self.lib.gp_bank_write(self._h, obj, tmpl0, n, feat.data_ptr(), layout, norm_passes, mask.data_ptr(),
+                                     mask.shape[1], mask.shape[2], _ptr(ist_feat), self.stream))
+
+    def set_poses(self, K: torch.Tensor, M: torch.Tensor, poses: torch.Tensor) -> None:
+        K, M, poses = (_f32(x, self.device).contiguous() for x in (K, M, poses))
+        assert K.shape == (self.O, 3, 3) and M.shape == (self.O, self.T_global, 3, 3)
+        assert poses.shape == (self.O, self.T_global, 4, 4)
+        check(self.lib.gp_bank_set_poses(self._h, K.data_ptr(), M.data_ptr(), poses.data_ptr(), self.stream))
+
+    def set_ist_weights(self, regressor) -> None:
+        """`regressor`: module with `scale_predictor` / `inplane_predictor` Sequentials (ist_net.py:140-155)."""
+        ws = []
+        for head in (regressor.scale_predictor, regressor.inplane_predictor):
+            for idx in (0, 2, 4):
+                ws.append(_f32(head[idx].weight.detach(), self.device).contiguous())
+                ws.append(_f32(head[idx].bias.detach(), self.device).contiguous())
+        assert ws[0].shape == (512, 512) and ws[2].shape == (256, 512) and ws[4].shape == (1, 256)
+        assert ws[6].shape == (512, 512) and ws[8].shape == (256, 512) and ws[10].shape == (2, 256)
+        self._keep = ws
+        arr = (C.c_void_p * 12)(*[w.data_ptr() for w in ws])
+        use_tanh = 1 if isinstance(regressor.inplane_predictor[-1], torch.nn.Tanh) else 0
+        check(self.lib.gp_set_ist_weights(self._h, arr, use_tanh))
+
+    # ------------------------------------------------------------------------------------------------ per batch
+    def set_queries(self, q_feat: torch.Tensor, q_mask: torch.Tensor, q_obj: torch.Tensor, norm_passes: int = 1) -> None:
+        q_feat, layout = _feature_layout(_f32(q_feat, self.device))
+        q_mask = _f32(q_mask, self.device).contiguous()
+        q_obj = q_obj.to(self.device, dtype=torch.int32).contiguous()
+        B = q_feat.shape[0]
+        assert q_mask.shape[0] == B and q_obj.shape == (B,)
+        check(self.lib.gp_set_queries(self._h, B, q_feat.data_ptr(), layout, norm_passes, q_mask.data_ptr(),
+                                      q_mask.shape[1], q_mask.shape[2], q_obj.data_ptr(), self.stream))
+        self._B = B
+
+    def _alloc_matches(self, B):
+        k = self.k
+        return dict(id_src=self._empty((B, k), torch.int64), score_src=self._empty((B, k), torch.float32),
+                    score_pts=self._empty((B, k, P), torch.float32), tar_pts=self._empty((B, k, P, 2), torch.int64),
+                    src_pts=self._empty((B, k, P, 2), torch.int64))
+
+    @staticmethod
+    def _matches_struct(m) -> GpMatches:
+        return GpMatches(m["id_src"].data_ptr(), m["score_src"].data_ptr(), m["score_pts"].data_ptr(),
+                         m["tar_pts"].data_ptr(), m["src_pts"].data_ptr())
+
+    def alloc_candidates(self, B, G=1):
+        k = self.k
+        return dict(score=self._empty((G, B, k), torch.float32), id=self._empty((G, B, k), torch.int32),
+                    pts_score=self._empty((G, B, k, P), torch.float32), idx=self._empty((G, B, k, P), torch.uint8),
+                    valid=self._empty((G, B, k, P), torch.uint8))
+
+    @staticmethod
+    def _cand_struct(c) -> GpCandidates:
+        return GpCandidates(c["score"].data_ptr(), c["id"].data_ptr(), c["pts_score"].data_ptr(), c["idx"].data_ptr(),
+                            c["valid"].data_ptr())
+
+    def sim_topk(self) -> Dict[str, torch.Tensor]:
+        """LocalSimilarity.test on the staged queries against the resident bank (single GPU)."""
+        m = self._alloc_matches(self._B)
+        ms = self._matches_struct(m)
+        check(self.lib.gp_sim_topk(self._h, self._B, C.byref(ms), self.stream))
+        return m
+
+    def sim_candidates(self, out=None) -> Dict[str, torch.Tensor]:
+        c = out if out is not None else self.alloc_candidates(self._B)
+        cs = self._cand_struct(c)
+        check(self.lib.gp_sim_candidates(self._h, self._B, C.byref(cs), self.stream))
+        return c
+
+    def topk_merge(self, gathered: Dict[str, torch.Tensor], G: int) -> Dict[str, torch.Tensor]:
+        m = self._alloc_matches(self._B)
+        cs, ms = self._cand_struct(gathered), self._matches_struct(m)
+        check(self.lib.gp_topk_merge(self._h, self._B, G, C.byref(cs), C.byref(ms), self.stream))
+        return m
+
+    def ist_mlp(self, q_ist: torch.Tensor, matches: Dict[str, torch.Tensor]):
+        q_ist = _f32(q_ist, self.device).contiguous()
+        B = self._B
+        assert q_ist.shape == (B, C_IST, 16, 16), tuple(q_ist.shape)
+        rel_scale = self._empty((B, self.k, P), torch.float32)
+        rel_inplane = self._empty((B, self.k, P, 2), torch.float32)
+        ms = self._matches_struct(matches)
+        check(self.lib.gp_ist_mlp(self._h, B, q_ist.data_ptr(), C.byref(ms), rel_scale.data_ptr(),
+                                  rel_inplane.data_ptr(), self.stream))
+        return rel_scale, rel_inplane
+
+    def _alloc_ransac(self, B):
+        k = self.k
+        return dict(M=self._empty((B, k, 3, 3), torch.float32), idx_failed=self._empty((B, k), torch.uint8),
+                    ransac_src_pts=self._empty((B, k, P, 2), torch.int64),
+                    ransac_tar_pts=self._empty((B, k, P, 2), torch.int64),
+                    ransac_scores=self._empty((B, k, P), torch.int64), inlier_count=self._empty((B, k), torch.int32))
+
+    @staticmethod
+    def _ransac_struct(r) -> GpRansacOut:
+        return GpRansacOut(r["M"].data_ptr(), r["idx_failed"].data_ptr(), r["ransac_src_pts"].data_ptr(),
+                           r["ransac_tar_pts"].data_ptr(), r["ransac_scores"].data_ptr(),
+                           r["inlier_count"].data_ptr() if "inlier_count" in r else None)
+
+    def ransac(self, matches, rel_scale, rel_inplane, B: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        B = B if B is not None else matches["src_pts"].shape[0]
+        r = self._alloc_ransac(B)
+        ms, rs = self._matches_struct(matches), self._ransac_struct(r)
+        check(self.lib.gp_ransac(self._h, B, C.byref(ms), rel_scale.data_ptr(), rel_inplane.data_ptr(), C.byref(rs),
+                                 self.stream))
+        return r
+
+    def sort_and_pose(self, q_K, q_M, matches, rel_scale, rel_inplane, ransac) -> Dict[str, torch.Tensor]:
+        B, k = self._B, self.k
+        q_K, q_M = _f32(q_K, self.device).contiguous(), _f32(q_M, self.device).contiguous()
+        out = self._alloc_matches(B)
+        out.update(relScale=self._empty((B, k, P), torch.float32), relInplane=self._empty((B, k, P, 2), torch.float32))
+        ro = self._alloc_ransac(B)
+        ro.pop("inlier_count")
+        out.update(ro)
+        out.update(scores=self._empty((B, k), torch.float32), pred_poses=self._empty((B, k, 4, 4), torch.float32))
+        pred = GpPredictions(self._matches_struct(out), out["relScale"].data_ptr(), out["relInplane"].data_ptr(),
+                             self._ransac_struct(out), out["scores"].data_ptr(), out["pred_poses"].data_ptr())
+        ms, rs = self._matches_struct(matches), self._ransac_struct(ransac)
+        check(self.lib.gp_sort_and_pose(self._h, B, q_K.data_ptr(), q_M.data_ptr(), C.byref(ms), rel_scale.data_ptr(),
+                                        rel_inplane.data_ptr(), C.byref(rs), C.byref(pred), self.stream))
+        out["idx_failed"] = out["idx_failed"].bool()
+        return out
+
+    def retrieve(self, q_feat, q_mask, q_obj, q_ist, q_K, q_M, norm_passes: int = 1) -> Dict[str, torch.Tensor]:
+        """Rows a3-a9 for one batch on one GPU: the tensor content of GigaPose.eval_retrieval (gigaPose.py:497-604)."""
+        self.set_queries(q_feat, q_mask, q_obj, norm_passes=norm_passes)
+        m = self.sim_topk()
+        rel_scale, rel_inplane = self.ist_mlp(q_ist, m)
+        r = self.ransac(m, rel_scale, rel_inplane)
+        return self.sort_and_pose(q_K, q_M, m, rel_scale, rel_inplane, r)
+
+    # ---------------------------------------------------------------------------------------------- diagnostics
+    def time_sim_kernel(self, iters: int = 10) -> float:
+        ms = C.c_float()
+        check(self.lib.gp_time_sim_kernel(self._h, self._B, iters, C.byref(ms), self.stream))
+        return ms.value
+
+    def debug_sim_tiles(self) -> torch.Tensor:
+        """Raw fp32 similarity tiles [T, B(sorted by object), 256 t, 256 s] (tests only, small sizes)."""
+        tiles = self._empty((self.T, self._B, P, P), torch.float32)
+        check(self.lib.gp_debug_sim_tiles(self._h, self._B, tiles.data_ptr(), self.stream))
+        return tiles
+
+    def launch_count(self) -> int:
+        return int(self.lib.gp_launch_count())
+
+    # algorithmic work of one similarity launch: 2*T*P^2*C per detection
+    def sim_flops(self, B: Optional[int] = None) -> float:
+        return 2.0 * (B or self._B) * self.T * P * P * C_AE

@@ -1,0 +1,176 @@
+/*
+ * gigapose_b200 -- C ABI of the B200-native GigaPose inference hot path (libgigapose_b200.so).
+ *
+ * The reference (nv-nguyen/gigapose) is pure Python: it has no FFI.  Its boundary for this path is a set of
+ * Python classes resolved by Hydra `_target_` strings (configs/model/large.yaml:1,36;
+ * configs/model/ae_net/dinov2_l.yaml:1; configs/model/ist_net/resnet.yaml:1,6,16).  The Python mirror of those
+ * classes lives in this repository under `src/` and calls the entry points below through ctypes
+ * (gigapose_b200/_lib.py); each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative gp_status; gp_last_error() gives the message
+ *    (thread local);  no C++ exceptions cross the boundary;
+ *  - all tensor pointers are DEVICE pointers owned by the caller; dense, row-major, the dtypes stated below;
+ *  - all work is enqueued on the caller's `stream` (a cudaStream_t passed as void*); no call synchronises the
+ *    host and no call allocates device memory: the bank and the workspace are caller-provided at gp_create and
+ *    sized by gp_query_sizes;
+ *  - one handle per (thread, GPU); a handle is not thread safe.
+ */
+#ifndef GIGAPOSE_B200_H_
+#define GIGAPOSE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GP_ABI_VERSION 1
+#define GP_NUM_PATCHES 256   /* 16 x 16 patches of a 224 x 224 crop, patch size 14 */
+#define GP_AE_DIM 1024       /* DINOv2 ViT-L/14 descriptor size (configs/model/ae_net/dinov2_l.yaml:10) */
+#define GP_IST_DIM 256       /* IST descriptor size (configs/model/ist_net/resnet.yaml:3) */
+
+typedef enum gp_status {
+  GP_OK = 0,
+  GP_ERR_INVALID = -1,       /* bad argument / configuration */
+  GP_ERR_CUDA = -2,          /* a CUDA runtime / driver call failed */
+  GP_ERR_UNSUPPORTED = -3,   /* not an sm_100 device, or driver without TMA descriptor support */
+  GP_ERR_STATE = -4          /* call order violated (e.g. search before queries were set) */
+} gp_status;
+
+typedef struct gp_context* gp_handle_t;
+
+/* feature layouts accepted by gp_bank_write / gp_set_queries */
+#define GP_LAYOUT_CHANNEL_MAJOR 0   /* [n, C, 16, 16]  -- what the reference modules exchange (ae_net.py:49-53) */
+#define GP_LAYOUT_PATCH_MAJOR 1     /* [n, 256, C]     -- ViT token order, kernel-native                       */
+
+/* precision of the similarity contraction */
+#define GP_PRECISION_FP32_SPLIT 0   /* bf16 hi/lo planes, hi*hi + hi*lo + lo*hi on tcgen05: fp32-faithful indices */
+#define GP_PRECISION_BF16 1         /* hi*hi only: plain bf16 tensor-core similarity (3x less tensor work)       */
+
+typedef struct gp_config {
+  int32_t abi_version;        /* GP_ABI_VERSION */
+  int32_t device;             /* CUDA device ordinal */
+  int32_t num_objects;        /* O */
+  int32_t num_templates;      /* templates per object held by THIS handle (T, or the shard size on multi-GPU) */
+  int32_t num_templates_global; /* templates per object over all shards (== num_templates on one GPU) */
+  int32_t template_id_stride; /* global template id = local id * stride + offset (template-interleaved shards) */
+  int32_t template_id_offset;
+  int32_t max_batch;          /* max detections per call */
+  int32_t top_k;              /* LocalSimilarity.k (configs/model/large.yaml:37), <= 32 */
+  float sim_threshold;        /* LocalSimilarity.sim_threshold (large.yaml:38) */
+  float patch_threshold;      /* LocalSimilarity.patch_threshold (large.yaml:39) */
+  float pixel_threshold;      /* RANSAC inlier threshold in pixels (poses.py:18) */
+  int32_t patch_size;         /* 14 */
+  int32_t precision;          /* GP_PRECISION_* */
+} gp_config_t;
+
+const char* gp_last_error(void);
+int gp_abi_version(void);
+
+/* Bytes the caller must provide for the template bank and for the per-call workspace. */
+int gp_query_sizes(const gp_config_t* cfg, size_t* bank_bytes, size_t* workspace_bytes);
+
+/* Creates a handle over caller-owned device memory (both 1024-byte aligned).  Replaces the template_data
+ * PandasTensorCollection + ObjectPoseRecovery built by GigaPose.set_template_data (gigaPose.py:383-394). */
+int gp_create(const gp_config_t* cfg, void* bank_mem, void* workspace_mem, gp_handle_t* out);
+int gp_destroy(gp_handle_t h);
+
+/* --- onboarding (gigaPose.py:357-398) -------------------------------------------------------------------- */
+
+/* Writes `n` templates of object `obj` starting at local template slot `tmpl0`.
+ *   feat      f32  descriptors, layout per `feat_layout`; L2-normalised `norm_passes` times on the way in
+ *             (2 = raw ViT tokens: ae_net.py:69 then matching.py:229; 1 = AENet output: matching.py:229 only)
+ *   mask      f32  [n, H, W] template masks; sampled nearest to 16x16 (matching.py:227)
+ *   ist_feat  f32  [n, 256, 16, 16] IST backbone features (gigaPose.py:376), may be NULL if a5 is not used */
+int gp_bank_write(gp_handle_t h, int obj, int tmpl0, int n, const float* feat, int feat_layout, int norm_passes,
+                  const float* mask, int H, int W, const float* ist_feat, void* stream);
+
+/* Pose tables over GLOBAL template ids (ObjectPoseRecovery ctor, poses.py:13-24):
+ *   K [O,3,3], M [O,Tg,3,3], poses [O,Tg,4,4], all f32. */
+int gp_bank_set_poses(gp_handle_t h, const float* K, const float* M, const float* poses, void* stream);
+
+/* IST regressor weights (ist_net.py:140-155), f32 device pointers in nn.Linear layout [out,in]; the pointers are
+ * retained (the caller keeps the tensors alive).  Order: scale {w1,b1,w2,b2,w3,b3}, inplane {w1,b1,w2,b2,w3,b3}. */
+int gp_set_ist_weights(gp_handle_t h, const float* const weights[12], int use_tanh);
+
+/* --- per batch of B detections ------------------------------------------------------------------------ */
+
+/* Stages the query descriptors / masks / object ids (gigaPose.py:513-522; matching.py:222-225).
+ *   q_feat f32 (layout/norm_passes as in gp_bank_write), q_mask f32 [B,H,W], q_obj int32 [B] 0-based. */
+int gp_set_queries(gp_handle_t h, int B, const float* q_feat, int feat_layout, int norm_passes, const float* q_mask,
+                   int H, int W, const int32_t* q_obj, void* stream);
+
+typedef struct gp_candidates {   /* compact per-shard top-k records, [B,k] leading dims */
+  float* score;                  /* [B,k]      per-template score (matching.py:274-278) */
+  int32_t* id;                   /* [B,k]      GLOBAL template id */
+  float* pts_score;              /* [B,k,256]  score_tar2src */
+  uint8_t* idx;                  /* [B,k,256]  idx_tar2src */
+  uint8_t* valid;                /* [B,k,256]  mask_all != 0 */
+} gp_candidates_t;
+
+typedef struct gp_matches {      /* exactly the outputs of LocalSimilarity.test (matching.py:308-316) */
+  int64_t* id_src;               /* [B,k] */
+  float* score_src;              /* [B,k] */
+  float* score_pts;              /* [B,k,256] */
+  int64_t* tar_pts;              /* [B,k,256,2] (x,y) patch coordinates, -1 = invalid */
+  int64_t* src_pts;              /* [B,k,256,2] */
+} gp_matches_t;
+
+/* Fused similarity search over this handle's templates + local top-k (matching.py:233-279). */
+int gp_sim_candidates(gp_handle_t h, int B, const gp_candidates_t* out, void* stream);
+/* Merges G candidate lists laid out [G][B][k] (G = 1: the local list; G > 1: after one all-gather over NVLink)
+ * and expands the winners (matching.py:279-316). */
+int gp_topk_merge(gp_handle_t h, int B, int G, const gp_candidates_t* gathered, const gp_matches_t* out, void* stream);
+/* Single-GPU convenience: gp_sim_candidates into the workspace + gp_topk_merge(G=1) == LocalSimilarity.test. */
+int gp_sim_topk(gp_handle_t h, int B, const gp_matches_t* out, void* stream);
+
+/* ISTNet.inference for all k hypotheses (ist_net.py:97-120; k-loop gigaPose.py:545-575).
+ *   q_ist f32 [B,256,16,16]; outputs rel_scale [B,k,256], rel_inplane [B,k,256,2] (-1000 where invalid).
+ * Every template named in m->id_src must be held by this handle. */
+int gp_ist_mlp(gp_handle_t h, int B, const float* q_ist, const gp_matches_t* m, float* rel_scale, float* rel_inplane,
+               void* stream);
+
+typedef struct gp_ransac_out {   /* ObjectPoseRecovery.forward_ransac (poses.py:124-163) */
+  float* M;                      /* [B,k,3,3] */
+  uint8_t* failed;               /* [B,k] */
+  int64_t* inlier_src_pts;       /* [B,k,256,2] */
+  int64_t* inlier_tar_pts;       /* [B,k,256,2] */
+  int64_t* inlier_scores;        /* [B,k,256] */
+  int32_t* inlier_count;         /* [B,k] */
+} gp_ransac_out_t;
+
+int gp_ransac(gp_handle_t h, int B, const gp_matches_t* m, const float* rel_scale, const float* rel_inplane,
+              const gp_ransac_out_t* out, void* stream);
+
+typedef struct gp_predictions {  /* every [B,k,...] tensor after the re-sort of gigaPose.py:588-595 + poses */
+  gp_matches_t matches;
+  float* rel_scale;              /* [B,k,256] */
+  float* rel_inplane;            /* [B,k,256,2] */
+  gp_ransac_out_t ransac;        /* inlier_count may be NULL */
+  float* scores;                 /* [B,k]  inliers / 256 (gigaPose.py:588) */
+  float* poses;                  /* [B,k,4,4] (poses.py:103-122) */
+} gp_predictions_t;
+
+/* scores, stable descending re-sort of the k hypotheses and pose lifting (gigaPose.py:588-604).
+ *   q_K, q_M f32 [B,3,3] query intrinsics / crop matrices. */
+int gp_sort_and_pose(gp_handle_t h, int B, const float* q_K, const float* q_M, const gp_matches_t* m,
+                     const float* rel_scale, const float* rel_inplane, const gp_ransac_out_t* r,
+                     const gp_predictions_t* out, void* stream);
+
+/* --- diagnostics ----------------------------------------------------------------------------------------- */
+/* number of kernels this library has launched since load (all handles); used for bench.py's `gpu_launches` */
+uint64_t gp_launch_count(void);
+/* times `iters` back-to-back runs of the similarity kernel alone with CUDA events on `stream`
+ * (synchronises the stream); writes the average milliseconds per launch. */
+int gp_time_sim_kernel(gp_handle_t h, int B, int iters, float* avg_ms, void* stream);
+
+/* test hook: runs the similarity kernel and additionally dumps the raw fp32 similarity tiles, laid out
+ * [item = n * B + j][256 t][256 s] where j indexes the queries sorted by object id (small sizes only). */
+int gp_debug_sim_tiles(gp_handle_t h, int B, float* tiles, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIGAPOSE_B200_H_ */

@@ -1,0 +1,140 @@
+"""-m gpu parity tests: the CUDA path (through the C ABI) against the CPU oracle and the reference-generated
+golden fixtures.  Bars: integer / index tensors bit-exact; floats within the tolerance written in each test."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gigapose_b200 import synth
+from oracle import port
+
+from helpers import FLOAT_KEYS, INT_KEYS, cpu, engine_from_case, run_engine
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_tiles(case, dtype=torch.float64):
+    """[T, B(sorted by object), 256 t, 256 s] similarity of the matching-time-normalised descriptors."""
+    order = torch.argsort(case.q_label, stable=True)
+    q = F.normalize(case.q_feat.to(dtype), dim=-1)[order]
+    bank = F.normalize(case.bank_feat.to(dtype), dim=-1)[case.q_label[order] - 1]       # [B,T,256,C]
+    return torch.einsum("btc,bnsc->nbts", q, bank)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32_split", 3e-6), ("bf16", 2e-2)])
+def test_similarity_tiles_against_fp64(precision, tol):
+    """The TMA + tcgen05 main loop alone: raw fp32 tiles vs an fp64 einsum on the same descriptors."""
+    case = synth.make_feature_case(B=3, O=2, T=6, seed=3)
+    eng = engine_from_case(case, precision=precision)
+    eng.set_queries(case.q_feat, case.q_mask16.reshape(-1, 16, 16), case.q_label - 1)
+    tiles = eng.debug_sim_tiles().cpu().double()
+    ref = _ref_tiles(case)
+    err = (tiles - ref).abs().max().item()
+    assert err < tol, f"{precision}: max |sim - fp64| = {err:.3e}"
+
+
+def _compare(out, ref, pose_tol=1e-3):
+    bad = {}
+    for k in INT_KEYS:
+        a, b = out[k], ref[k]
+        a = a.bool() if b.dtype == torch.bool else a
+        if not torch.equal(a, b.to(a.dtype)):
+            bad[k] = int((a != b.to(a.dtype)).sum())
+    for k in FLOAT_KEYS:
+        tol = pose_tol if k == "pred_poses" else 2e-5
+        scale = 1.0
+        if k == "pred_poses":                       # translations are in mm (~400): relative 1e-3 on t, abs on R
+            d = (out[k] - ref[k]).abs()
+            d[..., :3, 3] = d[..., :3, 3] / ref[k][..., :3, 3].abs().clamp(min=1.0)
+            err = d.max().item()
+        else:
+            err = ((out[k] - ref[k]).abs() / scale).max().item()
+        if not err < tol:
+            bad[k] = err
+    return bad
+
+
+@pytest.mark.parametrize("name", ["retrieval_c1", "retrieval_small"])
+def test_retrieval_matches_reference_golden(golden_dir, name):
+    """Whole a3-a9 chain on the GPU vs the outputs of the UNMODIFIED reference recorded in tests/golden."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    B, O, T, seed, _ = [int(x) for x in g["cfg"]]
+    case = synth.make_feature_case(B=B, O=O, T=T, seed=seed)
+    eng = engine_from_case(case, regressor=port.RegressorPort())
+    out = cpu(run_engine(eng, case))
+    ref = {k: torch.from_numpy(g[k]) for k in INT_KEYS + FLOAT_KEYS}
+    bad = _compare(out, ref)
+    assert not bad, f"mismatches vs reference golden: {bad}"
+
+
+def test_retrieval_matches_oracle_live():
+    """A second seed/shape, compared with the CPU oracle run on the spot (uneven object population)."""
+    labels = torch.tensor([1, 1, 1, 3, 3, 2, 1, 3, 3])
+    case = synth.make_feature_case(B=9, O=3, T=20, seed=21, labels=labels)
+    reg = port.RegressorPort(seed=4)
+    ref = port.retrieval(synth.to_reference_layout(case), reg)
+    eng = engine_from_case(case, regressor=reg)
+    out = cpu(run_engine(eng, case))
+    bad = _compare(out, ref)
+    assert not bad, f"mismatches vs CPU oracle: {bad}"
+    # planted structure: the best template of every object is the planted view
+    first = port.similarity_search(**{k: synth.to_reference_layout(case)[k] for k in
+                                      ("src_feats", "tar_feat", "src_masks", "tar_mask")})["id_src"][:, 0]
+    assert torch.equal(first, case.planted["best_template"][case.q_label - 1])
+
+
+def test_stagewise_against_oracle():
+    """Each stage fed with the ORACLE's inputs, so a failure names the stage."""
+    case = synth.make_feature_case(B=5, O=2, T=12, seed=33)
+    reg = port.RegressorPort(seed=6)
+    ri = synth.to_reference_layout(case)
+    sim = port.similarity_search(ri["src_feats"], ri["tar_feat"], ri["src_masks"], ri["tar_mask"])
+    eng = engine_from_case(case, regressor=reg)
+    eng.set_queries(case.q_feat, case.q_mask16.reshape(-1, 16, 16), case.q_label - 1)
+    # a4
+    m = eng.sim_topk()
+    for k in ("id_src", "tar_pts", "src_pts"):
+        assert torch.equal(m[k].cpu(), sim[k]), k
+    assert torch.allclose(m["score_src"].cpu(), sim["score_src"], atol=2e-6)
+    assert torch.allclose(m["score_pts"].cpu(), sim["score_pts"], atol=2e-6)
+    # a5 on the oracle's matches
+    dev = eng.device
+    m_ref = {k: v.to(dev) for k, v in sim.items()}
+    rs, ri_ = eng.ist_mlp(case.q_ist, m_ref)
+    B, K = sim["id_src"].shape
+    rs_ref = torch.zeros(B, K, 256)
+    ri_ref = torch.zeros(B, K, 256, 2)
+    bi = torch.arange(B)
+    for kk in range(K):
+        rs_ref[:, kk], ri_ref[:, kk] = port.ist_mlp(reg, ri["src_ist"][bi, sim["id_src"][:, kk]], ri["tar_ist"],
+                                                   sim["src_pts"][:, kk], sim["tar_pts"][:, kk])
+    assert torch.allclose(rs.cpu(), rs_ref, atol=2e-5, rtol=1e-5)
+    assert torch.allclose(ri_.cpu(), ri_ref, atol=2e-5, rtol=1e-5)
+    # a7 on the oracle's MLP outputs
+    r = eng.ransac(m_ref, rs_ref.to(dev), ri_ref.to(dev))
+    M, failed, in_src, in_tar, in_sc = port.ransac(sim["src_pts"], sim["tar_pts"], rs_ref, ri_ref)
+    assert torch.equal(r["idx_failed"].cpu().bool(), failed)
+    assert torch.equal(r["ransac_scores"].cpu(), in_sc)
+    assert torch.equal(r["ransac_src_pts"].cpu(), in_src)
+    assert torch.equal(r["ransac_tar_pts"].cpu(), in_tar)
+    assert torch.allclose(r["M"].cpu(), M, atol=1e-5)
+    assert torch.equal(r["inlier_count"].cpu().long(), in_sc.sum(-1))
+
+
+def test_empty_and_degenerate_queries():
+    """Edge cases: an all-zero query mask (no valid patch anywhere) and a single-template-valid query."""
+    case = synth.make_feature_case(B=3, O=1, T=8, seed=44)
+    case.q_mask16[1] = 0
+    reg = port.RegressorPort(seed=6)
+    ref = port.retrieval(synth.to_reference_layout(case), reg)
+    eng = engine_from_case(case, regressor=reg)
+    out = cpu(run_engine(eng, case))
+    # the masked query has no valid correspondence at all: identity M, not failed, zero scores
+    assert (out["src_pts"][1] == -1).all() and (out["tar_pts"][1] == -1).all()
+    assert torch.equal(out["M"][1], torch.eye(3).expand(5, 3, 3))
+    assert not out["idx_failed"][1].any()
+    assert (out["scores"][1] == 0).all()
+    for k in ("tar_pts", "src_pts", "ransac_scores", "idx_failed"):
+        assert torch.equal(out[k][[0, 2]].to(ref[k].dtype), ref[k][[0, 2]]), k
