@@ -64,8 +64,10 @@ SYMBOLS = {
     "gp_topk_merge": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(GpCandidates), C.POINTER(GpMatches), C.c_void_p]),
     "gp_sim_topk": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GpMatches), C.c_void_p]),
     "gp_ist_mlp": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(GpMatches), C.c_void_p, C.c_void_p, C.c_void_p]),
-    "gp_ransac": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GpMatches), C.c_void_p, C.c_void_p, C.POINTER(GpRansacOut),
-                            C.c_void_p]),
+    "gp_ransac": (C.c_int, [C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                            C.POINTER(GpRansacOut), C.c_void_p]),
+    "gp_pose_recover": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gp_sort_and_pose": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(GpMatches), C.c_void_p,
                                    C.c_void_p, C.POINTER(GpRansacOut), C.POINTER(GpPredictions), C.c_void_p]),
     "gp_launch_count": (C.c_uint64, []),

@@ -384,14 +384,16 @@ int gp_ist_mlp(gp_handle_t h, int B, const float* q_ist, const gp_matches_t* m, 
   return GP_OK;
 }
 
-int gp_ransac(gp_handle_t h, int B, const gp_matches_t* m, const float* rel_scale, const float* rel_inplane,
-              const gp_ransac_out_t* out, void* stream) {
-  if (!h || !m || !rel_scale || !rel_inplane || !out || !out->inlier_count) return fail(GP_ERR_INVALID, "null argument");
-  if (B < 1) return fail(GP_ERR_INVALID, "B must be >= 1");
+int gp_ransac(int n, float pixel_threshold, int patch_size, const int64_t* src_pts, const int64_t* tar_pts,
+              const float* rel_scale, const float* rel_inplane, const gp_ransac_out_t* out, void* stream) {
+  if (!src_pts || !tar_pts || !rel_scale || !rel_inplane || !out || !out->inlier_count || !out->M || !out->failed ||
+      !out->inlier_src_pts || !out->inlier_tar_pts || !out->inlier_scores)
+    return fail(GP_ERR_INVALID, "null argument");
+  if (n < 1) return fail(GP_ERR_INVALID, "n must be >= 1");
   gp::RansacParams p;
-  p.B = B; p.k = h->cfg.top_k; p.pixel_threshold = h->cfg.pixel_threshold; p.patch_size = h->cfg.patch_size;
-  p.src_pts = reinterpret_cast<const long long*>(m->src_pts);
-  p.tar_pts = reinterpret_cast<const long long*>(m->tar_pts);
+  p.n = n; p.pixel_threshold = pixel_threshold; p.patch_size = patch_size;
+  p.src_pts = reinterpret_cast<const long long*>(src_pts);
+  p.tar_pts = reinterpret_cast<const long long*>(tar_pts);
   p.rel_scale = rel_scale; p.rel_inplane = rel_inplane;
   p.M = out->M; p.failed = out->failed;
   p.in_src = reinterpret_cast<long long*>(out->inlier_src_pts);
@@ -399,6 +401,18 @@ int gp_ransac(gp_handle_t h, int B, const gp_matches_t* m, const float* rel_scal
   p.in_score = reinterpret_cast<long long*>(out->inlier_scores);
   p.in_count = out->inlier_count;
   GP_CUDA(gp::launch_ransac(p, static_cast<cudaStream_t>(stream)));
+  g_launches += 1;
+  return GP_OK;
+}
+
+int gp_pose_recover(int B, int k, int num_templates, const int32_t* q_obj, const float* q_K, const float* q_M,
+                    const int64_t* id_src, const float* M, const float* tmpl_K, const float* tmpl_M,
+                    const float* tmpl_pose, float* poses, void* stream) {
+  if (!q_obj || !q_K || !q_M || !id_src || !M || !tmpl_K || !tmpl_M || !tmpl_pose || !poses)
+    return fail(GP_ERR_INVALID, "null argument");
+  if (B < 1 || k < 1 || num_templates < 1) return fail(GP_ERR_INVALID, "B, k and num_templates must be >= 1");
+  GP_CUDA(gp::launch_pose_only(B * k, k, num_templates, q_obj, q_K, q_M, reinterpret_cast<const long long*>(id_src), M,
+                               tmpl_K, tmpl_M, tmpl_pose, poses, static_cast<cudaStream_t>(stream)));
   g_launches += 1;
   return GP_OK;
 }

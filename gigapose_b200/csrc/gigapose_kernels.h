@@ -101,7 +101,7 @@ cudaError_t launch_ist_mlp(const IstMlpWeights& w, const IstMlpParams& p, cudaSt
 
 // ---------------------------------------------------------------- RANSAC + scoring + pose lifting (ransac_pose.cu)
 struct RansacParams {
-  int B, k;
+  int n;                      // number of (detection, hypothesis) pairs
   float pixel_threshold;      // 14 px (poses.py:18)
   int patch_size;             // 14
   const long long* src_pts;   // [B,k,256,2]
@@ -142,5 +142,8 @@ struct PoseParams {
   float* o_poses;             // [B,k,4,4]
 };
 cudaError_t launch_sort_and_pose(const PoseParams& p, cudaStream_t stream);
+cudaError_t launch_pose_only(int n, int k, int T, const int* q_obj, const float* q_K, const float* q_M,
+                             const long long* id_src, const float* M, const float* tmpl_K, const float* tmpl_M,
+                             const float* tmpl_pose, float* poses, cudaStream_t stream);
 
 }  // namespace gp

@@ -149,6 +149,56 @@ __device__ __forceinline__ void mat3_mul(const float* A, const float* B, float* 
     for (int j = 0; j < 3; ++j) C[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
 }
 
+// (template id, 2-D similarity M, crop matrices, intrinsics) -> 4x4 pose (poses.py:26-101)
+__device__ __forceinline__ void lift_pose(const float* Kt, const float* Mt, const float* Pt, const float* M,
+                                          const float* Kq, const float* Mq, float* out) {
+  // in-plane rotation = first 2x2 block of M divided by the norm of its first column (lib3d/torch.py:150-162)
+  const float sc = sqrtf(M[0] * M[0] + M[3] * M[3]);
+  const float Rin[9] = {M[0] / sc, M[1] / sc, 0.f, M[3] / sc, M[4] / sc, 0.f, 0.f, 0.f, 1.f};
+  float Rt[9], R[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Rt[i * 3 + j] = Pt[i * 4 + j];
+  mat3_mul(Rin, Rt, R);                                       // poses.py:69-71
+  const float tz = Pt[11];
+  // template centre projected with the template intrinsics (poses.py:74-77)
+  float c[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c[i] = Kt[i * 3] * Pt[3] + Kt[i * 3 + 1] * Pt[7] + Kt[i * 3 + 2] * Pt[11];
+  const float cz = c[2];
+  c[0] /= cz; c[1] /= cz; c[2] /= cz;
+  // inverse of the scale+translation query crop matrix (lib3d/torch.py:47-65), then affine2d = Mq^-1 . M . Mt
+  const float qs = Mq[0];
+  const float Minv[9] = {1.f / qs, 0.f, -Mq[2] / qs, 0.f, 1.f / qs, -Mq[5] / qs, 0.f, 0.f, 1.f};
+  float T1[9], A[9];
+  mat3_mul(Minv, M, T1);
+  mat3_mul(T1, Mt, A);
+  float qc[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) qc[i] = A[i * 3] * c[0] + A[i * 3 + 1] * c[1] + A[i * 3 + 2] * c[2];
+  // general 3x3 inverse of the query intrinsics (torch.inverse, poses.py:89)
+  const float a = Kq[0], bb = Kq[1], cc = Kq[2], d = Kq[3], e = Kq[4], f = Kq[5], g = Kq[6], h = Kq[7], i9 = Kq[8];
+  const float det = a * (e * i9 - f * h) - bb * (d * i9 - f * g) + cc * (d * h - e * g);
+  const float id = 1.f / det;
+  const float Ki[9] = {(e * i9 - f * h) * id, (cc * h - bb * i9) * id, (bb * f - cc * e) * id,
+                       (f * g - d * i9) * id, (a * i9 - cc * g) * id, (cc * d - a * f) * id,
+                       (d * h - e * g) * id, (bb * g - a * h) * id, (a * e - bb * d) * id};
+  const float s2d = sqrtf(A[0] * A[0] + A[3] * A[3]);        // poses.py:92
+  const float qz = (tz / s2d) * (Kq[0] / Kt[0]);              // poses.py:93-94
+  float tr[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) tr[i] = Ki[i * 3] * qc[0] + Ki[i * 3 + 1] * qc[1] + Ki[i * 3 + 2] * qc[2];
+  const float trz = tr[2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) tr[i] = (tr[i] / trz) * qz;     // poses.py:97-99
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    out[i * 4 + 0] = R[i * 3 + 0]; out[i * 4 + 1] = R[i * 3 + 1]; out[i * 4 + 2] = R[i * 3 + 2]; out[i * 4 + 3] = tr[i];
+  }
+  out[12] = Pt[12]; out[13] = Pt[13]; out[14] = Pt[14]; out[15] = Pt[15];
+}
+
 __global__ void __launch_bounds__(256)
 sort_and_pose_kernel(PoseParams p) {
   __shared__ int s_order[32];
@@ -189,66 +239,40 @@ sort_and_pose_kernel(PoseParams p) {
     const size_t src = (size_t)b * k + s_order[t], dst = (size_t)b * k + t;
     const int o = p.q_obj[b];
     const long long view = p.id_src[src];
-    const float* Kt = p.tmpl_K + (size_t)o * 9;
-    const float* Mt = p.tmpl_M + ((size_t)o * p.T + view) * 9;
-    const float* Pt = p.tmpl_pose + ((size_t)o * p.T + view) * 16;
-    const float* M = p.M + src * 9;
-    const float* Kq = p.q_K + (size_t)b * 9;
-    const float* Mq = p.q_M + (size_t)b * 9;
-    float* out = p.o_poses + dst * 16;
-    // in-plane rotation = first 2x2 block of M divided by the norm of its first column (lib3d/torch.py:150-162)
-    const float sc = sqrtf(M[0] * M[0] + M[3] * M[3]);
-    const float Rin[9] = {M[0] / sc, M[1] / sc, 0.f, M[3] / sc, M[4] / sc, 0.f, 0.f, 0.f, 1.f};
-    float Rt[9], R[9];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) Rt[i * 3 + j] = Pt[i * 4 + j];
-    mat3_mul(Rin, Rt, R);                                       // poses.py:69-71
-    const float tz = Pt[11];
-    // template centre projected with the template intrinsics (poses.py:74-77)
-    float c[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) c[i] = Kt[i * 3] * Pt[3] + Kt[i * 3 + 1] * Pt[7] + Kt[i * 3 + 2] * Pt[11];
-    const float cz = c[2];
-    c[0] /= cz; c[1] /= cz; c[2] /= cz;
-    // inverse of the scale+translation query crop matrix (lib3d/torch.py:47-65), then affine2d = Mq^-1 . M . Mt
-    const float qs = Mq[0];
-    const float Minv[9] = {1.f / qs, 0.f, -Mq[2] / qs, 0.f, 1.f / qs, -Mq[5] / qs, 0.f, 0.f, 1.f};
-    float T1[9], A[9];
-    mat3_mul(Minv, M, T1);
-    mat3_mul(T1, Mt, A);
-    float qc[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) qc[i] = A[i * 3] * c[0] + A[i * 3 + 1] * c[1] + A[i * 3 + 2] * c[2];
-    // general 3x3 inverse of the query intrinsics (torch.inverse, poses.py:89)
-    const float a = Kq[0], bb = Kq[1], cc = Kq[2], d = Kq[3], e = Kq[4], f = Kq[5], g = Kq[6], h = Kq[7], i9 = Kq[8];
-    const float det = a * (e * i9 - f * h) - bb * (d * i9 - f * g) + cc * (d * h - e * g);
-    const float id = 1.f / det;
-    const float Ki[9] = {(e * i9 - f * h) * id, (cc * h - bb * i9) * id, (bb * f - cc * e) * id,
-                         (f * g - d * i9) * id, (a * i9 - cc * g) * id, (cc * d - a * f) * id,
-                         (d * h - e * g) * id, (bb * g - a * h) * id, (a * e - bb * d) * id};
-    const float s2d = sqrtf(A[0] * A[0] + A[3] * A[3]);        // poses.py:92
-    const float qz = (tz / s2d) * (Kq[0] / Kt[0]);              // poses.py:93-94
-    float tr[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) tr[i] = Ki[i * 3] * qc[0] + Ki[i * 3 + 1] * qc[1] + Ki[i * 3 + 2] * qc[2];
-    const float trz = tr[2];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) tr[i] = (tr[i] / trz) * qz;     // poses.py:97-99
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      out[i * 4 + 0] = R[i * 3 + 0]; out[i * 4 + 1] = R[i * 3 + 1]; out[i * 4 + 2] = R[i * 3 + 2]; out[i * 4 + 3] = tr[i];
-    }
-    out[12] = Pt[12]; out[13] = Pt[13]; out[14] = Pt[14]; out[15] = Pt[15];
+    lift_pose(p.tmpl_K + (size_t)o * 9, p.tmpl_M + ((size_t)o * p.T + view) * 9,
+              p.tmpl_pose + ((size_t)o * p.T + view) * 16, p.M + src * 9, p.q_K + (size_t)b * 9, p.q_M + (size_t)b * 9,
+              p.o_poses + dst * 16);
   }
+}
+
+// ObjectPoseRecovery.forward_recovery alone (poses.py:103-122): one thread per (detection, hypothesis)
+__global__ void pose_only_kernel(int n, int k, int T, const int* __restrict__ q_obj, const float* __restrict__ q_K,
+                                 const float* __restrict__ q_M, const long long* __restrict__ id_src,
+                                 const float* __restrict__ M, const float* __restrict__ tmpl_K,
+                                 const float* __restrict__ tmpl_M, const float* __restrict__ tmpl_pose,
+                                 float* __restrict__ poses) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = i / k;
+  const int o = q_obj[b];
+  const long long view = id_src[i];
+  lift_pose(tmpl_K + (size_t)o * 9, tmpl_M + ((size_t)o * T + view) * 9, tmpl_pose + ((size_t)o * T + view) * 16,
+            M + (size_t)i * 9, q_K + (size_t)b * 9, q_M + (size_t)b * 9, poses + (size_t)i * 16);
 }
 
 }  // namespace
 
 cudaError_t launch_ransac(const RansacParams& p, cudaStream_t stream) {
-  if (p.B * p.k <= 0) return cudaSuccess;
-  ransac_kernel<<<p.B * p.k, 256, 0, stream>>>(p);
+  if (p.n <= 0) return cudaSuccess;
+  ransac_kernel<<<p.n, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pose_only(int n, int k, int T, const int* q_obj, const float* q_K, const float* q_M,
+                             const long long* id_src, const float* M, const float* tmpl_K, const float* tmpl_M,
+                             const float* tmpl_pose, float* poses, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  pose_only_kernel<<<(n + 127) / 128, 128, 0, stream>>>(n, k, T, q_obj, q_K, q_M, id_src, M, tmpl_K, tmpl_M, tmpl_pose, poses);
   return cudaGetLastError();
 }
 

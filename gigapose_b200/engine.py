@@ -42,6 +42,14 @@ def _feature_layout(feat: torch.Tensor):
     return feat.contiguous(), LAYOUT_PATCH_MAJOR
 
 
+def ransac_points(lib, src_pts, tar_pts, rel_scale, rel_inplane, out, pixel_threshold, patch_size, stream):
+    """gp_ransac over n = prod(leading dims) (detection, hypothesis) pairs; tensors [..., 256, 2] / [..., 256]."""
+    n = src_pts.numel() // (P * 2)
+    rs = Engine._ransac_struct(out)
+    check(lib.gp_ransac(n, float(pixel_threshold), int(patch_size), src_pts.data_ptr(), tar_pts.data_ptr(),
+                        rel_scale.data_ptr(), rel_inplane.data_ptr(), C.byref(rs), stream))
+
+
 class Engine:
     """One template bank (or one shard of it) resident on one B200 plus the per-batch workspace."""
 
@@ -210,12 +218,11 @@ class Engine:
                            r["ransac_tar_pts"].data_ptr(), r["ransac_scores"].data_ptr(),
                            r["inlier_count"].data_ptr() if "inlier_count" in r else None)
 
-    def ransac(self, matches, rel_scale, rel_inplane, B: Optional[int] = None) -> Dict[str, torch.Tensor]:
-        B = B if B is not None else matches["src_pts"].shape[0]
+    def ransac(self, matches, rel_scale, rel_inplane) -> Dict[str, torch.Tensor]:
+        B = matches["src_pts"].shape[0]
         r = self._alloc_ransac(B)
-        ms, rs = self._matches_struct(matches), self._ransac_struct(r)
-        check(self.lib.gp_ransac(self._h, B, C.byref(ms), rel_scale.data_ptr(), rel_inplane.data_ptr(), C.byref(rs),
-                                 self.stream))
+        ransac_points(self.lib, matches["src_pts"], matches["tar_pts"], rel_scale, rel_inplane, r,
+                      self.cfg.pixel_threshold, self.cfg.patch_size, self.stream)
         return r
 
     def sort_and_pose(self, q_K, q_M, matches, rel_scale, rel_inplane, ransac) -> Dict[str, torch.Tensor]:
@@ -261,3 +268,55 @@ class Engine:
     # algorithmic work of one similarity launch: 2*T*P^2*C per detection
     def sim_flops(self, B: Optional[int] = None) -> float:
         return 2.0 * (B or self._B) * self.T * P * P * C_AE
+
+
+# ------------------------------------------------------------------------------------------------------------
+# explicit-input entry points behind the reference's module-level APIs (no resident bank): a cached scratch
+# Engine with one "object" per query holds the gathered templates, exactly like the reference's per-call gather
+# ------------------------------------------------------------------------------------------------------------
+_SCRATCH = {}
+
+
+def _scratch_engine(device, B, T, k, **cfg) -> Engine:
+    key = (str(device), B, T, k, tuple(sorted(cfg.items())))
+    eng = _SCRATCH.get(key)
+    if eng is None:
+        _SCRATCH.clear()                      # keep at most one scratch bank alive
+        eng = Engine(B, T, B, device=device, k=k, **cfg)
+        _SCRATCH[key] = eng
+    return eng
+
+
+def similarity_search_explicit(src_feats, tar_feat, src_masks, tar_mask, k, sim_threshold, patch_threshold,
+                               precision="fp32_split") -> Dict[str, torch.Tensor]:
+    """LocalSimilarity.test on explicit tensors: src_feats [B,N,C,16,16], tar_feat [B,C,16,16],
+    src_masks [B,N,H,W], tar_mask [B,H,W] (matching.py:188-316)."""
+    B, N = src_feats.shape[:2]
+    eng = _scratch_engine(src_feats.device, B, N, k, sim_threshold=sim_threshold, patch_threshold=patch_threshold,
+                          precision=precision)
+    for b in range(B):
+        eng.bank_write(b, 0, src_feats[b], src_masks[b], norm_passes=1)
+    eng.set_queries(tar_feat, tar_mask, torch.arange(B, device=src_feats.device), norm_passes=1)
+    return eng.sim_topk()
+
+
+def ist_mlp_explicit(regressor, src_feat, tar_feat, src_pts, tar_pts):
+    """ISTNet.inference on explicit tensors (ist_net.py:97-120): src_feat/tar_feat [B,256,16,16], pts [B,N,2]."""
+    B, N = src_pts.shape[:2]
+    assert N == P, "one correspondence slot per patch"
+    dev = src_feat.device
+    eng = _scratch_engine(dev, B, 1, 1)
+    eng.set_ist_weights(regressor)
+    ist = _f32(src_feat, eng.device).contiguous()
+    zeros_feat = torch.zeros(1, P, C_AE, device=eng.device)
+    ones_mask = torch.ones(1, 16, 16, device=eng.device)
+    for b in range(B):
+        eng.bank_write(b, 0, zeros_feat, ones_mask, ist_feat=ist[b:b + 1], norm_passes=0)
+    eng.set_queries(torch.zeros(B, P, C_AE, device=eng.device), torch.ones(B, 16, 16, device=eng.device),
+                    torch.arange(B, device=eng.device), norm_passes=0)
+    m = dict(id_src=torch.zeros(B, 1, dtype=torch.int64, device=eng.device),
+             src_pts=src_pts.to(eng.device).reshape(B, 1, P, 2).contiguous(),
+             tar_pts=tar_pts.to(eng.device).reshape(B, 1, P, 2).contiguous(),
+             score_src=torch.zeros(B, 1, device=eng.device), score_pts=torch.zeros(B, 1, P, device=eng.device))
+    rs, ri = eng.ist_mlp(tar_feat, m)
+    return rs.reshape(B, P), ri.reshape(B, P, 2)

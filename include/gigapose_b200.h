@@ -141,8 +141,16 @@ typedef struct gp_ransac_out {   /* ObjectPoseRecovery.forward_ransac (poses.py:
   int32_t* inlier_count;         /* [B,k] */
 } gp_ransac_out_t;
 
-int gp_ransac(gp_handle_t h, int B, const gp_matches_t* m, const float* rel_scale, const float* rel_inplane,
-              const gp_ransac_out_t* out, void* stream);
+/* n = number of (detection, hypothesis) pairs; src_pts/tar_pts [n,256,2] i64, rel_scale [n,256], rel_inplane
+ * [n,256,2]; outputs as gp_ransac_out_t with leading dimension n.  Needs no handle (RANSAC.forward, ransac.py:108). */
+int gp_ransac(int n, float pixel_threshold, int patch_size, const int64_t* src_pts, const int64_t* tar_pts,
+              const float* rel_scale, const float* rel_inplane, const gp_ransac_out_t* out, void* stream);
+
+/* ObjectPoseRecovery.forward_recovery alone (poses.py:103-122), no re-sort: q_obj int32 [B] 0-based, q_K/q_M
+ * [B,3,3], id_src i64 [B,k], M [B,k,3,3], template tables K [O,3,3], M [O,T,3,3], poses [O,T,4,4] -> poses [B,k,4,4]. */
+int gp_pose_recover(int B, int k, int num_templates, const int32_t* q_obj, const float* q_K, const float* q_M,
+                    const int64_t* id_src, const float* M, const float* tmpl_K, const float* tmpl_M,
+                    const float* tmpl_pose, float* poses, void* stream);
 
 typedef struct gp_predictions {  /* every [B,k,...] tensor after the re-sort of gigaPose.py:588-595 + poses */
   gp_matches_t matches;

@@ -1,0 +1,127 @@
+"""-m gpu tests of the reference-facing Python surface (`src/models/**`): same calls the reference makes, results
+against the CPU oracle."""
+import pandas as pd
+import pytest
+import torch
+
+from gigapose_b200 import synth
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _case():
+    case = synth.make_feature_case(B=4, O=2, T=10, seed=8)
+    return case, synth.to_reference_layout(case)
+
+
+def test_local_similarity_test_signature_and_outputs():
+    from src.models.matching import LocalSimilarity
+    case, ri = _case()
+    metric = LocalSimilarity(k=5, sim_threshold=0.5, patch_threshold=3)
+    out = metric.test(src_feats=ri["src_feats"].to(DEV), tar_feat=ri["tar_feat"].to(DEV),
+                      src_masks=ri["src_masks"].to(DEV), tar_mask=ri["tar_mask"].to(DEV), max_batch_size=None)
+    ref = port.similarity_search(ri["src_feats"], ri["tar_feat"], ri["src_masks"], ri["tar_mask"])
+    assert out.id_src.dtype == torch.int64 and out.tar_pts.shape == (4, 5, 256, 2)
+    for k in ("id_src", "tar_pts", "src_pts"):
+        assert torch.equal(getattr(out, k).cpu(), ref[k]), k
+    assert torch.allclose(out.score_src.cpu(), ref["score_src"], atol=2e-6)
+    assert torch.allclose(out.score_pts.cpu(), ref["score_pts"], atol=2e-6)
+
+
+def test_istnet_inference_and_pose_recovery_modules():
+    import src.megapose.utils.tensor_collection as tc
+    from src.models.network.ist_net import ISTNet, Regressor
+    from src.models.network.resnet import ResNet
+    from src.models.poses import ObjectPoseRecovery
+    case, ri = _case()
+    sim = port.similarity_search(ri["src_feats"], ri["tar_feat"], ri["src_masks"], ri["tar_mask"])
+    reg_ref = port.RegressorPort(seed=12)
+    reg = Regressor(descriptor_size=256, hidden_dim=256, use_tanh_act=True, normalize_output=True)
+    reg.load_state_dict(reg_ref.state_dict())
+    backbone = ResNet(dict(n_heads=0, input_dim=3, input_size=256, initial_dim=128, block_dims=[128, 192, 256, 512],
+                           descriptor_size=256))
+    ist = ISTNet("resnet", backbone, reg, max_batch_size=64)
+    ist.regressor.load_state_dict(reg_ref.state_dict())      # ISTNet re-initialises Linear layers (ist_net.py:33-42)
+    ist = ist.to(DEV).eval()
+    B, K = sim["id_src"].shape
+    bi = torch.arange(B)
+    rel_scale = torch.zeros(B, K, 256)
+    rel_inpl = torch.zeros(B, K, 256, 2)
+    for kk in range(K):
+        src_ist = ri["src_ist"][bi, sim["id_src"][:, kk]]
+        a, b = ist.inference(src_feat=src_ist.to(DEV), tar_feat=ri["tar_ist"].to(DEV),
+                             src_pts=sim["src_pts"][:, kk].to(DEV), tar_pts=sim["tar_pts"][:, kk].to(DEV))
+        ra, rb = port.ist_mlp(reg_ref, src_ist, ri["tar_ist"], sim["src_pts"][:, kk], sim["tar_pts"][:, kk])
+        assert torch.allclose(a.cpu(), ra, atol=2e-5, rtol=1e-5) and torch.allclose(b.cpu(), rb, atol=2e-5, rtol=1e-5)
+        rel_scale[:, kk], rel_inpl[:, kk] = ra, rb
+    # ObjectPoseRecovery: forward_ransac on a collection, then forward_recovery
+    rec = ObjectPoseRecovery(template_K=ri["template_K"].to(DEV), template_Ms=ri["template_Ms"].to(DEV),
+                             template_poses=ri["template_poses"].to(DEV))
+    pred = tc.PandasTensorCollection(infos=pd.DataFrame(), src_pts=sim["src_pts"].to(DEV), tar_pts=sim["tar_pts"].to(DEV),
+                                     relScale=rel_scale.to(DEV), relInplane=rel_inpl.to(DEV))
+    pred = rec.forward_ransac(pred)
+    M, failed, in_src, in_tar, in_sc = port.ransac(sim["src_pts"], sim["tar_pts"], rel_scale, rel_inpl)
+    assert torch.equal(pred.idx_failed.cpu(), failed)
+    assert torch.equal(pred.ransac_scores.cpu(), in_sc) and torch.equal(pred.ransac_src_pts.cpu(), in_src)
+    assert torch.allclose(pred.M.cpu(), M, atol=1e-5, rtol=1e-5)
+    poses = rec.forward_recovery(tar_label=ri["tar_label"].to(DEV), tar_K=ri["tar_K"].to(DEV), tar_M=ri["tar_M"].to(DEV),
+                                 pred_src_views=sim["id_src"].to(DEV), pred_M=pred.M.clone())
+    ref = port.pose_recovery(ri["tar_label"], ri["tar_K"], ri["tar_M"], sim["id_src"], M, ri["template_K"],
+                             ri["template_Ms"], ri["template_poses"])
+    err = (poses.cpu() - ref).abs()
+    err[..., :3, 3] /= ref[..., :3, 3].abs().clamp(min=1.0)
+    assert float(err.max()) < 1e-3
+
+
+def test_ransac_module_single_hypothesis():
+    import src.megapose.utils.tensor_collection as tc
+    from src.models.ransac import RANSAC
+    g = torch.Generator().manual_seed(0)
+    B, N = 3, 256
+    # planted similarity: tar = s * R(theta) * src + t on a subset of patches, exact relScale / relInplane
+    src = torch.full((B, N, 2), -1, dtype=torch.long)
+    tar = torch.full((B, N, 2), -1, dtype=torch.long)
+    rs = torch.full((B, N), -1000.0)
+    ri = torch.full((B, N, 2), -1000.0)
+    for b in range(B):
+        idx = torch.randperm(N, generator=g)[:60].sort().values
+        sx, sy = idx % 16, idx // 16
+        shift = torch.tensor([1, -2][b % 2])
+        src[b, idx, 0], src[b, idx, 1] = sx, sy
+        tar[b, idx, 0], tar[b, idx, 1] = (sx + shift).clamp(0, 15), sy
+        rs[b, idx] = 1.0
+        ri[b, idx, 0], ri[b, idx, 1] = 1.0, 0.0
+    batch = tc.PandasTensorCollection(infos=pd.DataFrame(), src_pts=src.to(DEV), tar_pts=tar.to(DEV), relScale=rs.to(DEV),
+                                      relInplane=ri.to(DEV))
+    Ms, failed, inl = RANSAC(pixel_threshold=14)(batch)
+    M_ref, failed_ref, in_src, in_tar, in_sc = port.ransac(src[:, None], tar[:, None], rs[:, None], ri[:, None])
+    assert torch.equal(failed.cpu(), failed_ref[:, 0])
+    assert torch.allclose(Ms.cpu(), M_ref[:, 0], atol=1e-5)
+    assert torch.equal(inl.src_pts.cpu(), in_src[:, 0]) and torch.equal(inl.scores.cpu(), in_sc[:, 0])
+    # known answer: pure translation by 14 * shift pixels
+    assert torch.allclose(Ms[:, 0, 2].cpu(), torch.tensor([14.0, -28.0, 14.0]))
+
+
+def test_gigapose_module_end_to_end_small():
+    """Crops in, poses out through the reference-facing `GigaPose` surface with synthetic templates."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    model = bench.build_models(torch.device(DEV))
+    templates = bench.SyntheticTemplates(2, 8, torch.device(DEV))
+    model.template_datasets = {"synthetic": templates}
+    model.test_dataset_name = "synthetic"
+    batch, labels, views = bench.make_queries(templates, 3, seed=1)
+    _, pred = model.eval_retrieval(batch, idx_batch=0, dataset_name="synthetic")
+    assert pred.pred_poses.shape == (3, 5, 4, 4) and pred.scores.shape == (3, 5)
+    assert torch.isfinite(pred.pred_poses).all()
+    # each query is a noisy copy of template `views[b]` of its object: that view must be among the k retrieved
+    assert bool((pred.id_src.cpu() == views[:, None]).any(dim=1).all())
+    # scores are sorted descending (gigaPose.py:590-595)
+    s = pred.scores.cpu()
+    assert bool((s[:, :-1] >= s[:, 1:]).all())
+    # oracle for the matching stage on the GPU-computed features of the same crops
+    eng = model.engines["synthetic"]
+    assert eng.launch_count() > 0
