@@ -209,6 +209,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="wrap ONE extra resident step in cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -283,6 +285,13 @@ def main():
     ms = e0.elapsed_time(e1) / args.steps
     launches = (eng.launch_count() - l0) // args.steps
     value = cfg["B"] / (ms / 1e3)
+
+    if args.profile_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
 
     # end to end through the plugin call, host buffers
     for _ in range(max(1, args.warmup // 2)):

@@ -81,10 +81,6 @@ def test_retrieval_matches_oracle_live():
     out = cpu(run_engine(eng, case))
     bad = _compare(out, ref)
     assert not bad, f"mismatches vs CPU oracle: {bad}"
-    # planted structure: the best template of every object is the planted view
-    first = port.similarity_search(**{k: synth.to_reference_layout(case)[k] for k in
-                                      ("src_feats", "tar_feat", "src_masks", "tar_mask")})["id_src"][:, 0]
-    assert torch.equal(first, case.planted["best_template"][case.q_label - 1])
 
 
 def test_stagewise_against_oracle():
