@@ -29,7 +29,7 @@ class GpConfig(C.Structure):
 
 class GpCandidates(C.Structure):
     _fields_ = [("score", C.c_void_p), ("id", C.c_void_p), ("pts_score", C.c_void_p), ("idx", C.c_void_p),
-                ("valid", C.c_void_p)]
+                ("valid", C.c_void_p), ("rel_scale", C.c_void_p), ("rel_inplane", C.c_void_p)]
 
 
 class GpMatches(C.Structure):
@@ -61,7 +61,8 @@ SYMBOLS = {
     "gp_set_queries": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p]),
     "gp_sim_candidates": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GpCandidates), C.c_void_p]),
-    "gp_topk_merge": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(GpCandidates), C.POINTER(GpMatches), C.c_void_p]),
+    "gp_topk_merge": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(GpCandidates), C.c_size_t, C.POINTER(GpMatches),
+                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "gp_sim_topk": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GpMatches), C.c_void_p]),
     "gp_ist_mlp": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(GpMatches), C.c_void_p, C.c_void_p, C.c_void_p]),
     "gp_ransac": (C.c_int, [C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -64,13 +64,14 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 plane [rows, 1024] (K contiguous); box = 32 columns (64 B, SWIZZLE_64B) x 256 rows = one patch set
-int make_plane_map(CUtensorMap* map, void* ptr, uint64_t rows) {
+// 2-D bf16 plane [rows, 1024] (K contiguous); box = 32 columns (64 B, SWIZZLE_64B) x box_rows rows
+// (256 = all patches of a template, 128 = one t-half of a query)
+int make_plane_map(CUtensorMap* map, void* ptr, uint64_t rows, uint32_t box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(GP_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from this driver");
   cuuint64_t dims[2] = {GP_AE_DIM, rows};
   cuuint64_t strides[1] = {GP_AE_DIM * sizeof(uint16_t)};
-  cuuint32_t box[2] = {32, 256};
+  cuuint32_t box[2] = {32, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -210,8 +211,8 @@ int gp_create(const gp_config_t* cfg, void* bank_mem, void* workspace_mem, gp_ha
   const uint64_t bank_rows = (uint64_t)cfg->num_objects * cfg->num_templates * GP_NUM_PATCHES;
   const uint64_t q_rows = (uint64_t)cfg->max_batch * GP_NUM_PATCHES;
   int e;
-  if ((e = make_plane_map(&h->tm_t_hi, h->bank.hi, bank_rows)) || (e = make_plane_map(&h->tm_t_lo, h->bank.lo, bank_rows)) ||
-      (e = make_plane_map(&h->tm_q_hi, h->ws.q_hi, q_rows)) || (e = make_plane_map(&h->tm_q_lo, h->ws.q_lo, q_rows))) {
+  if ((e = make_plane_map(&h->tm_t_hi, h->bank.hi, bank_rows, 256)) || (e = make_plane_map(&h->tm_t_lo, h->bank.lo, bank_rows, 256)) ||
+      (e = make_plane_map(&h->tm_q_hi, h->ws.q_hi, q_rows, 128)) || (e = make_plane_map(&h->tm_q_lo, h->ws.q_lo, q_rows, 128))) {
     delete h;
     return e;
   }
@@ -342,12 +343,15 @@ int gp_sim_candidates(gp_handle_t h, int B, const gp_candidates_t* out, void* st
   return GP_OK;
 }
 
-int gp_topk_merge(gp_handle_t h, int B, int G, const gp_candidates_t* g, const gp_matches_t* out, void* stream) {
+int gp_topk_merge(gp_handle_t h, int B, int G, const gp_candidates_t* g, size_t rank_stride_bytes,
+                  const gp_matches_t* out, float* out_rel_scale, float* out_rel_inplane, void* stream) {
   if (!h || !g || !out) return fail(GP_ERR_INVALID, "null argument");
   if (B < 1 || G < 1 || G * h->cfg.top_k > 64) return fail(GP_ERR_INVALID, "B=%d G=%d: need G*k <= 64", B, G);
   gp::TopkMergeParams m;
-  m.B = B; m.k = h->cfg.top_k; m.G = G;
+  m.B = B; m.k = h->cfg.top_k; m.G = G; m.rank_stride_bytes = rank_stride_bytes;
   m.cand_score = g->score; m.cand_id = g->id; m.cand_pts_score = g->pts_score; m.cand_idx = g->idx; m.cand_valid = g->valid;
+  m.cand_rel_scale = g->rel_scale; m.cand_rel_inplane = g->rel_inplane;
+  m.out_rel_scale = out_rel_scale; m.out_rel_inplane = out_rel_inplane;
   m.id_src = reinterpret_cast<long long*>(out->id_src); m.score_src = out->score_src; m.score_pts = out->score_pts;
   m.tar_pts = reinterpret_cast<long long*>(out->tar_pts); m.src_pts = reinterpret_cast<long long*>(out->src_pts);
   GP_CUDA(gp::launch_topk_merge_expand(m, static_cast<cudaStream_t>(stream)));
@@ -359,8 +363,9 @@ int gp_sim_topk(gp_handle_t h, int B, const gp_matches_t* out, void* stream) {
   if (!h || !out) return fail(GP_ERR_INVALID, "null argument");
   gp_candidates_t c;
   c.score = h->ws.c_score; c.id = h->ws.c_id; c.pts_score = h->ws.c_pts_score; c.idx = h->ws.c_idx; c.valid = h->ws.c_valid;
+  c.rel_scale = nullptr; c.rel_inplane = nullptr;
   if (int e = gp_sim_candidates(h, B, &c, stream)) return e;
-  return gp_topk_merge(h, B, 1, &c, out, stream);
+  return gp_topk_merge(h, B, 1, &c, 0, out, nullptr, nullptr, stream);
 }
 
 int gp_ist_mlp(gp_handle_t h, int B, const float* q_ist, const gp_matches_t* m, float* rel_scale, float* rel_inplane,

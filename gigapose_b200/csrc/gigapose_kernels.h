@@ -44,12 +44,17 @@ struct TopkSelectParams {
 cudaError_t launch_topk_select(const TopkSelectParams& p, cudaStream_t stream);
 
 struct TopkMergeParams {
-  int B, k, G;                // G candidate lists laid out [G][B][k]
+  int B, k, G;                // G candidate lists; list g of a field starts rank_stride_bytes * g after the field base
+  size_t rank_stride_bytes;   // 0 = every field is a dense [G][B][k][...] array
   const float* cand_score;
   const int* cand_id;
   const float* cand_pts_score;
   const uint8_t* cand_idx;
   const uint8_t* cand_valid;
+  const float* cand_rel_scale;    // nullable [.,B,k,256]   per-candidate IST outputs computed by the owning shard
+  const float* cand_rel_inplane;  // nullable [.,B,k,256,2]
+  float* out_rel_scale;           // nullable [B,k,256]
+  float* out_rel_inplane;         // nullable [B,k,256,2]
   long long* id_src;          // [B,k]
   float* score_src;           // [B,k]
   float* score_pts;           // [B,k,256]

@@ -3,9 +3,10 @@
 //
 // One work item = one (query b, template n) pair = one 256(t) x 256(s) x 1024(c) similarity tile.
 // A persistent CTA per SM walks the item list:
-//   warp 0   : TMA producer  -- streams K-blocks of the query / template descriptor planes into a 3-stage smem ring
-//   warp 1   : UMMA issuer   -- tcgen05.mma (cta_group::1, M=128, N=256, K=16, bf16 -> fp32) into TMEM;
-//                               the two t-halves of the tile live in TMEM columns [0,256) and [256,512)
+//   warp 0   : TMA producer  -- streams K-blocks of the query / template descriptor planes into a 4-stage smem ring
+//   warp 1   : UMMA issuer   -- tcgen05.mma (cta_group::1, M=128, N=256, K=16, bf16 -> fp32) into TMEM; the two
+//                               t-halves of a tile run back to back into alternating 256-column accumulators, so
+//                               the epilogue of one half overlaps the tensor work of the next
 //   warp 2   : TMEM allocator
 //   warps 4-11: epilogue     -- tcgen05.ld the fp32 tile, apply masks + threshold (matching.py:234-236), row
 //                               max/arg-max (t->s) in registers, column max/arg-max (s->t) with redux.sync +
@@ -29,28 +30,34 @@ constexpr int kP = 256;                         // patches per crop (16 x 16)
 constexpr int kC = 1024;                        // descriptor channels
 constexpr int kBlockK = 32;                     // bf16 elements per stage row: 64 B = SWIZZLE_64B span
 constexpr int kRowBytes = kBlockK * 2;
-constexpr int kStages = 3;
-constexpr int kPlaneBytes = kP * kRowBytes;     // 16 KB: 256 rows x 64 B
-constexpr int kStageBytes = 4 * kPlaneBytes;    // q_hi, q_lo, t_hi, t_lo
+constexpr int kStages = 4;
+constexpr int kHalfRows = 128;                  // t-rows per UMMA (M = 128)
+constexpr int kQPlaneBytes = kHalfRows * kRowBytes;   // 8 KB : 128 query rows x 64 B
+constexpr int kTPlaneBytes = kP * kRowBytes;          // 16 KB: 256 template rows x 64 B
+constexpr int kStageBytes = 2 * kQPlaneBytes + 2 * kTPlaneBytes;   // q_hi, q_lo, t_hi, t_lo = 48 KB
 constexpr int kNumKBlocks = kC / kBlockK;       // 32
 constexpr int kEpiWarps = 8;
-constexpr int kEpiThreads = kEpiWarps * 32;     // 256 == kP: epilogue thread i owns query patch t = i
+constexpr int kEpiThreads = kEpiWarps * 32;     // 256
 constexpr int kThreads = 4 * 32 + kEpiThreads;  // 384
-constexpr int kTmemCols = 512;
+constexpr int kTmemCols = 512;                  // two 128 x 256 fp32 accumulators (double buffered)
 constexpr uint32_t kIdesc = umma_idesc_f16(128, 256, /*bf16*/ 1);
 
 struct __align__(8) SimSmemTail {
   float smask[kP];                              // template mask sampled at 16x16 (float: alpha masks are not binary)
   float tmask[kP];                              // query mask sampled at 16x16
-  float pmax[kEpiWarps][kP];                    // per-epilogue-warp partial column max (32 t-rows each)
+  float pmax[kEpiWarps][kP];                    // partial column max per group of 32 t-rows (group = t / 32)
   float cmax[kP];                               // score_src2tar
+  float rmax_s[kP];                             // score_tar2src
+  float rowp_max[2][2][kHalfRows];              // [t-half][column half][row]: partial row maxima
   float red[2][kEpiWarps];
   uint8_t pidx[kEpiWarps][kP];
   uint8_t cidx[kP];                             // idx_src2tar
+  uint8_t ridx_s[kP];                           // idx_tar2src
+  uint8_t rowp_idx[2][2][kHalfRows];
   uint64_t full_bar[kStages];
   uint64_t empty_bar[kStages];
-  uint64_t tmem_full_bar;
-  uint64_t tmem_empty_bar;
+  uint64_t tmem_full_bar[2];
+  uint64_t tmem_empty_bar[2];
   uint32_t tmem_base;
 };
 
@@ -58,6 +65,10 @@ constexpr int kSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + si
 
 }  // namespace
 
+// Work unit of the producer / UMMA warps: (item, t-half) = a 128(t) x 256(s) x 1024(c) half tile.  The two halves of
+// a tile run back to back into alternating TMEM accumulators, so the epilogue of one half overlaps the tensor work
+// of the next (the template planes are streamed once per half: L2 -> SM traffic is not the limiter, see profiles/).
+template <bool kDebug>
 __global__ void __launch_bounds__(kThreads, 1)
 sim_search_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
                   const __grid_constant__ CUtensorMap tm_t_hi, const __grid_constant__ CUtensorMap tm_t_lo,
@@ -76,8 +87,10 @@ sim_search_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
       mbar_init(&tail.full_bar[s], 1);
       mbar_init(&tail.empty_bar[s], 1);
     }
-    mbar_init(&tail.tmem_full_bar, 1);
-    mbar_init(&tail.tmem_empty_bar, kEpiWarps);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tail.tmem_full_bar[a], 1);
+      mbar_init(&tail.tmem_empty_bar[a], kEpiWarps);
+    }
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -99,23 +112,25 @@ sim_search_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = (passes == 3 ? 4 : 2) * kPlaneBytes;
+      const uint32_t tx_bytes = (passes == 3 ? 2 : 1) * (kQPlaneBytes + kTPlaneBytes);
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         const int n = item / p.B;
         const int b = p.perm[item - n * p.B];
-        const int q_row = b * kP;
         const int t_row = (p.q_obj[b] * p.T + n) * kP;
-        for (int kb = 0; kb < kNumKBlocks; ++kb) {
-          mbar_wait(&tail.empty_bar[stage], phase ^ 1);
-          uint8_t* st = smem + stage * kStageBytes;
-          mbar_arrive_expect_tx(&tail.full_bar[stage], tx_bytes);
-          tma_load_2d(st + 0 * kPlaneBytes, &tm_q_hi, &tail.full_bar[stage], kb * kBlockK, q_row);
-          tma_load_2d(st + 2 * kPlaneBytes, &tm_t_hi, &tail.full_bar[stage], kb * kBlockK, t_row);
-          if (passes == 3) {
-            tma_load_2d(st + 3 * kPlaneBytes, &tm_t_lo, &tail.full_bar[stage], kb * kBlockK, t_row);
-            tma_load_2d(st + 1 * kPlaneBytes, &tm_q_lo, &tail.full_bar[stage], kb * kBlockK, q_row);
+        for (int half = 0; half < 2; ++half) {
+          const int q_row = b * kP + half * kHalfRows;
+          for (int kb = 0; kb < kNumKBlocks; ++kb) {
+            mbar_wait(&tail.empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * kStageBytes;
+            mbar_arrive_expect_tx(&tail.full_bar[stage], tx_bytes);
+            tma_load_2d(st, &tm_q_hi, &tail.full_bar[stage], kb * kBlockK, q_row);
+            tma_load_2d(st + 2 * kQPlaneBytes, &tm_t_hi, &tail.full_bar[stage], kb * kBlockK, t_row);
+            if (passes == 3) {
+              tma_load_2d(st + 2 * kQPlaneBytes + kTPlaneBytes, &tm_t_lo, &tail.full_bar[stage], kb * kBlockK, t_row);
+              tma_load_2d(st + kQPlaneBytes, &tm_q_lo, &tail.full_bar[stage], kb * kBlockK, q_row);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -123,103 +138,124 @@ sim_search_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
     // ======================================= UMMA issuer ========================================
     if (lane == 0) {
       int stage = 0;
-      uint32_t phase = 0, tphase = 0;
+      uint32_t phase = 0;
+      uint32_t unit = 0;                                          // running half-tile counter
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        mbar_wait(&tail.tmem_empty_bar, tphase ^ 1);          // epilogue has drained the previous tile
-        tc_fence_after();
-        for (int kb = 0; kb < kNumKBlocks; ++kb) {
-          mbar_wait(&tail.full_bar[stage], phase);
+        for (int half = 0; half < 2; ++half, ++unit) {
+          const uint32_t acc = unit & 1u;
+          mbar_wait(&tail.tmem_empty_bar[acc], ((unit >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
           tc_fence_after();
-          const uint32_t st = smem_u32(smem + stage * kStageBytes);
-          const uint32_t q_hi = st, q_lo = st + kPlaneBytes, t_hi = st + 2 * kPlaneBytes, t_lo = st + 3 * kPlaneBytes;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const uint32_t d = tmem_base + half * 256;
-            const uint32_t aoff = half * (128 * kRowBytes);
+          const uint32_t d = tmem_base + acc * 256;
+          for (int kb = 0; kb < kNumKBlocks; ++kb) {
+            mbar_wait(&tail.full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + stage * kStageBytes);
+            const uint32_t q_hi = st, q_lo = st + kQPlaneBytes, t_hi = st + 2 * kQPlaneBytes,
+                           t_lo = st + 2 * kQPlaneBytes + kTPlaneBytes;
 #pragma unroll
             for (int pass = 0; pass < 3; ++pass) {
               if (pass < passes) {
-                const uint32_t a = (pass == 2 ? q_lo : q_hi) + aoff;
+                const uint32_t a = (pass == 2 ? q_lo : q_hi);
                 const uint32_t bsm = (pass == 1 ? t_lo : t_hi);
 #pragma unroll
                 for (int k16 = 0; k16 < kBlockK / 16; ++k16) {
-                  const uint32_t acc = (kb | pass | k16) != 0 ? 1u : 0u;
+                  const uint32_t accum = (kb | pass | k16) != 0 ? 1u : 0u;
                   umma_f16(d, umma_desc_kmajor<kRowBytes>(a + k16 * 32), umma_desc_kmajor<kRowBytes>(bsm + k16 * 32),
-                           kIdesc, acc);
+                           kIdesc, accum);
                 }
               }
             }
+            umma_commit(&tail.empty_bar[stage]);                  // frees the smem stage once these MMAs retire
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tail.empty_bar[stage]);                  // frees the smem stage once these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          umma_commit(&tail.tmem_full_bar[acc]);                  // accumulator complete -> epilogue
         }
-        umma_commit(&tail.tmem_full_bar);                       // accumulators complete -> epilogue
-        tphase ^= 1;
       }
     }
   } else if (warp >= 4) {
     // ========================================= epilogue =========================================
-    const int e = warp - 4;                  // 0..7 ; TMEM lane quarter = warp % 4 = e % 4, t-half = e / 4
-    const int t = e * 32 + lane;             // query patch owned by this thread (row of the tile)
-    const uint32_t taddr = tmem_base + ((uint32_t)((e & 3) * 32) << 16) + (uint32_t)((e >> 2) * 256);
+    // warp e: TMEM lane quarter q = e % 4 (rows 32q..32q+31 of the half tile), column half ch = e / 4.
+    const int e = warp - 4;
+    const int q = e & 3, ch = e >> 2;
+    const int tid = e * 32 + lane;           // 0..255: also "patch owned by this thread" in the per-tile tail
+    const int r = q * 32 + lane;             // row within the half tile
     const float thr = p.sim_threshold;
-    uint32_t tphase = 0;
+    uint32_t unit = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int n = item / p.B;
       const int b = p.perm[item - n * p.B];
       const size_t rec = (size_t)b * p.T + n;
-      tail.smask[t] = p.bank_mask[((size_t)p.q_obj[b] * p.T + n) * kP + t];
-      const float tm = p.q_mask[(size_t)b * kP + t];
-      tail.tmask[t] = tm;
+      tail.smask[tid] = p.bank_mask[((size_t)p.q_obj[b] * p.T + n) * kP + tid];
+      tail.tmask[tid] = p.q_mask[(size_t)b * kP + tid];
       named_barrier_sync(1, kEpiThreads);
 
-      mbar_wait(&tail.tmem_full_bar, tphase);
-      tphase ^= 1;
-      tc_fence_after();
-
-      float rmax = -1.0f;                    // all candidates are >= 0 after thresholding -> first max wins
-      int ridx = 0;
+      for (int half = 0; half < 2; ++half, ++unit) {
+        const uint32_t acc = unit & 1u;
+        const int t = half * kHalfRows + r;                     // query patch of this thread's row
+        const float tm = tail.tmask[t];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + ch * 128;
+        mbar_wait(&tail.tmem_full_bar[acc], (unit >> 1) & 1u);
+        tc_fence_after();
+        float rmax = -1.0f;                  // all candidates are >= 0 after thresholding -> first max wins
+        int ridx = 0;
 #pragma unroll 1
-      for (int c0 = 0; c0 < kP; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c0, r);
-        tmem_ld_wait();
-        uint32_t keep_m = 0, keep_i = 0;
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v32[32];
+          tmem_ld_32x32(taddr + c0, v32);
+          tmem_ld_wait();
+          const int s0 = ch * 128 + c0;
+          uint32_t keep_m = 0, keep_b = 1;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (p.debug_tile) p.debug_tile[((size_t)item * kP + t) * kP + c0 + j] = __uint_as_float(r[j]);
-          float v = __uint_as_float(r[j]) * tail.smask[c0 + j];          // matching.py:234
-          v = v * tm;                                                     // matching.py:235
-          v = (v < thr) ? 0.0f : v;                                       // matching.py:236
-          if (v > rmax) { rmax = v; ridx = c0 + j; }                      // torch.max(dim=3): first maximum
-          const uint32_t bits = __float_as_uint(v);                       // v >= 0: float order == uint order
-          const uint32_t m = __reduce_max_sync(0xffffffffu, bits);
-          const uint32_t bal = __ballot_sync(0xffffffffu, bits == m);
-          if (lane == j) { keep_m = m; keep_i = __ffs(bal) - 1; }         // torch.max(dim=2): first maximum
+          for (int j = 0; j < 32; ++j) {
+            if (kDebug) p.debug_tile[((size_t)item * kP + t) * kP + s0 + j] = __uint_as_float(v32[j]);
+            float v = __uint_as_float(v32[j]) * tail.smask[s0 + j];          // matching.py:234
+            v = v * tm;                                                       // matching.py:235
+            v = (v < thr) ? 0.0f : v;                                         // matching.py:236
+            if (v > rmax) { rmax = v; ridx = s0 + j; }                        // torch.max(dim=3): first maximum
+            const uint32_t bits = __float_as_uint(v);                         // v >= 0: float order == uint order
+            const uint32_t m = __reduce_max_sync(0xffffffffu, bits);
+            const uint32_t bal = __ballot_sync(0xffffffffu, bits == m);
+            if (lane == j) { keep_m = m; keep_b = bal; }                      // lane j keeps column s0 + j
+          }
+          const int g = half * 4 + q;                                         // group of 32 t-rows: t / 32
+          tail.pmax[g][s0 + lane] = __uint_as_float(keep_m);
+          tail.pidx[g][s0 + lane] = (uint8_t)(g * 32 + __ffs(keep_b) - 1);   // torch.max(dim=2): first maximum
         }
-        tail.pmax[e][c0 + lane] = __uint_as_float(keep_m);
-        tail.pidx[e][c0 + lane] = (uint8_t)(e * 32 + keep_i);
+        tail.rowp_max[half][ch][r] = rmax;
+        tail.rowp_idx[half][ch][r] = (uint8_t)ridx;
+        // accumulator fully read: hand it back to the UMMA warp before the smem-only part
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail.tmem_empty_bar[acc]);
+        named_barrier_sync(1, kEpiThreads);
+        if (ch == 0) {                        // merge the two column halves of row r (ties: lower s wins)
+          float a = tail.rowp_max[half][0][r];
+          uint8_t ai = tail.rowp_idx[half][0][r];
+          const float c = tail.rowp_max[half][1][r];
+          if (c > a) { a = c; ai = tail.rowp_idx[half][1][r]; }
+          tail.rmax_s[t] = a;
+          tail.ridx_s[t] = ai;
+        }
       }
-      // TMEM fully read: hand the accumulators back to the MMA warp before the (smem-only) tail of the epilogue
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tail.tmem_empty_bar);
-      named_barrier_sync(1, kEpiThreads);
 
       {  // combine the 8 partial column maxima in ascending-t order (strict > keeps the first maximum)
-        float best = tail.pmax[0][t];
-        uint8_t bi = tail.pidx[0][t];
+        float best = tail.pmax[0][tid];
+        uint8_t bi = tail.pidx[0][tid];
 #pragma unroll
         for (int g = 1; g < kEpiWarps; ++g) {
-          const float v = tail.pmax[g][t];
-          if (v > best) { best = v; bi = tail.pidx[g][t]; }
+          const float v = tail.pmax[g][tid];
+          if (v > best) { best = v; bi = tail.pidx[g][tid]; }
         }
-        tail.cmax[t] = best;
-        tail.cidx[t] = bi;
+        tail.cmax[tid] = best;
+        tail.cidx[tid] = bi;
       }
       named_barrier_sync(1, kEpiThreads);
 
-      // matching.py:247-271 for query patch t
+      // matching.py:247-271 for query patch t = tid
+      const int t = tid;
+      const float rmax = tail.rmax_s[t];
+      const int ridx = tail.ridx_s[t];
+      const float tm = tail.tmask[t];
       const bool mask_sim = rmax >= thr;
       const int back = tail.cidx[ridx];                                   // idx_src2tar[idx_tar2src[t]]
       const float dx = (float)(back & 15) - (float)(t & 15);
@@ -324,22 +360,29 @@ topk_select_kernel(TopkSelectParams p) {
 // reference's output format (matching.py:282-316, format_prediction :29-61):
 //   id_src[B,k] i64, score_src[B,k] f32, score_pts[B,k,256] f32, tar_pts/src_pts[B,k,256,2] i64 (-1 = invalid).
 // Candidates are laid out [G][B][k]; ordering = score descending, then global template id ascending.
+template <typename T>
+__device__ __forceinline__ const T* rank_ptr(const T* base, int g, size_t rank_stride_bytes, size_t dense_elems) {
+  return rank_stride_bytes ? reinterpret_cast<const T*>(reinterpret_cast<const char*>(base) + (size_t)g * rank_stride_bytes)
+                           : base + (size_t)g * dense_elems;
+}
+
 __global__ void __launch_bounds__(256)
 topk_merge_expand_kernel(TopkMergeParams p) {
   __shared__ int s_sel[32];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int ncand = p.G * p.k;
+  const size_t bk = (size_t)p.B * p.k;
   if (tid == 0) {
-    // tiny selection sort over <= 8*k candidates
-    unsigned long long used = 0;   // supports ncand <= 64
+    // tiny selection sort over <= 64 candidates: score descending, then global template id ascending
+    unsigned long long used = 0;
     for (int kk = 0; kk < p.k; ++kk) {
       float bv = 0.f; int bid = 0; int bc = -1;
       for (int c = 0; c < ncand; ++c) {
         if (used >> c & 1ull) continue;
         const int g = c / p.k, j = c - g * p.k;
-        const size_t o = ((size_t)g * p.B + b) * p.k + j;
-        const float v = p.cand_score[o];
-        const int id = p.cand_id[o];
+        const size_t o = (size_t)b * p.k + j;
+        const float v = rank_ptr(p.cand_score, g, p.rank_stride_bytes, bk)[o];
+        const int id = rank_ptr(p.cand_id, g, p.rank_stride_bytes, bk)[o];
         if (bc < 0 || v > bv || (v == bv && id < bid)) { bv = v; bid = id; bc = c; }
       }
       used |= 1ull << bc;
@@ -350,16 +393,16 @@ topk_merge_expand_kernel(TopkMergeParams p) {
   for (int kk = 0; kk < p.k; ++kk) {
     const int c = s_sel[kk];
     const int g = c / p.k, j = c - g * p.k;
-    const size_t o = ((size_t)g * p.B + b) * p.k + j;
+    const size_t o = (size_t)b * p.k + j;
     const size_t dst = (size_t)b * p.k + kk;
     if (tid == 0) {
-      p.id_src[dst] = (long long)p.cand_id[o];
-      p.score_src[dst] = p.cand_score[o];
+      p.id_src[dst] = (long long)rank_ptr(p.cand_id, g, p.rank_stride_bytes, bk)[o];
+      p.score_src[dst] = rank_ptr(p.cand_score, g, p.rank_stride_bytes, bk)[o];
     }
     const int t = tid;
-    const bool valid = p.cand_valid[o * kP + t] != 0;
-    const int s = p.cand_idx[o * kP + t];
-    p.score_pts[dst * kP + t] = p.cand_pts_score[o * kP + t];
+    const bool valid = rank_ptr(p.cand_valid, g, p.rank_stride_bytes, bk * kP)[o * kP + t] != 0;
+    const int s = rank_ptr(p.cand_idx, g, p.rank_stride_bytes, bk * kP)[o * kP + t];
+    p.score_pts[dst * kP + t] = rank_ptr(p.cand_pts_score, g, p.rank_stride_bytes, bk * kP)[o * kP + t];
     longlong2 tp, sp;
     tp.x = valid ? (long long)(t & 15) : -1ll;
     tp.y = valid ? (long long)(t >> 4) : -1ll;
@@ -367,6 +410,11 @@ topk_merge_expand_kernel(TopkMergeParams p) {
     sp.y = valid ? (long long)(s >> 4) : -1ll;
     reinterpret_cast<longlong2*>(p.tar_pts)[dst * kP + t] = tp;
     reinterpret_cast<longlong2*>(p.src_pts)[dst * kP + t] = sp;
+    if (p.out_rel_scale && p.cand_rel_scale)
+      p.out_rel_scale[dst * kP + t] = rank_ptr(p.cand_rel_scale, g, p.rank_stride_bytes, bk * kP)[o * kP + t];
+    if (p.out_rel_inplane && p.cand_rel_inplane)
+      reinterpret_cast<float2*>(p.out_rel_inplane)[dst * kP + t] =
+          reinterpret_cast<const float2*>(rank_ptr(p.cand_rel_inplane, g, p.rank_stride_bytes, bk * kP * 2))[o * kP + t];
   }
 }
 
@@ -377,13 +425,18 @@ cudaError_t launch_sim_search(const CUtensorMap& q_hi, const CUtensorMap& q_lo, 
                               const CUtensorMap& t_lo, const SimSearchParams& p, int num_sms, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(sim_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(sim_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(sim_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   if (p.num_items <= 0) return cudaSuccess;
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
-  sim_search_kernel<<<grid, kThreads, kSmemBytes, stream>>>(q_hi, q_lo, t_hi, t_lo, p);
+  if (p.debug_tile)
+    sim_search_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(q_hi, q_lo, t_hi, t_lo, p);
+  else
+    sim_search_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(q_hi, q_lo, t_hi, t_lo, p);
   return cudaGetLastError();
 }
 

@@ -173,7 +173,7 @@ class Engine:
     @staticmethod
     def _cand_struct(c) -> GpCandidates:
         return GpCandidates(c["score"].data_ptr(), c["id"].data_ptr(), c["pts_score"].data_ptr(), c["idx"].data_ptr(),
-                            c["valid"].data_ptr())
+                            c["valid"].data_ptr(), _ptr(c.get("rel_scale")), _ptr(c.get("rel_inplane")))
 
     def sim_topk(self) -> Dict[str, torch.Tensor]:
         """LocalSimilarity.test on the staged queries against the resident bank (single GPU)."""
@@ -188,11 +188,19 @@ class Engine:
         check(self.lib.gp_sim_candidates(self._h, self._B, C.byref(cs), self.stream))
         return c
 
-    def topk_merge(self, gathered: Dict[str, torch.Tensor], G: int) -> Dict[str, torch.Tensor]:
-        m = self._alloc_matches(self._B)
+    def topk_merge(self, gathered: Dict[str, torch.Tensor], G: int, rank_stride_bytes: int = 0):
+        """Global top-k over G candidate lists.  Returns the matches and, when the candidates carry the per-shard IST
+        outputs, the winners' (rel_scale, rel_inplane)."""
+        B = self._B
+        m = self._alloc_matches(B)
         cs, ms = self._cand_struct(gathered), self._matches_struct(m)
-        check(self.lib.gp_topk_merge(self._h, self._B, G, C.byref(cs), C.byref(ms), self.stream))
-        return m
+        rs = ri = None
+        if gathered.get("rel_scale") is not None:
+            rs = self._empty((B, self.k, P), torch.float32)
+            ri = self._empty((B, self.k, P, 2), torch.float32)
+        check(self.lib.gp_topk_merge(self._h, B, G, C.byref(cs), rank_stride_bytes, C.byref(ms), _ptr(rs), _ptr(ri),
+                                     self.stream))
+        return (m, rs, ri) if rs is not None else m
 
     def ist_mlp(self, q_ist: torch.Tensor, matches: Dict[str, torch.Tensor]):
         q_ist = _f32(q_ist, self.device).contiguous()

@@ -108,6 +108,8 @@ typedef struct gp_candidates {   /* compact per-shard top-k records, [B,k] leadi
   float* pts_score;              /* [B,k,256]  score_tar2src */
   uint8_t* idx;                  /* [B,k,256]  idx_tar2src */
   uint8_t* valid;                /* [B,k,256]  mask_all != 0 */
+  float* rel_scale;              /* [B,k,256]   optional (NULL): IST outputs of the candidate, filled by the owning shard */
+  float* rel_inplane;            /* [B,k,256,2] optional (NULL) */
 } gp_candidates_t;
 
 typedef struct gp_matches {      /* exactly the outputs of LocalSimilarity.test (matching.py:308-316) */
@@ -120,9 +122,13 @@ typedef struct gp_matches {      /* exactly the outputs of LocalSimilarity.test 
 
 /* Fused similarity search over this handle's templates + local top-k (matching.py:233-279). */
 int gp_sim_candidates(gp_handle_t h, int B, const gp_candidates_t* out, void* stream);
-/* Merges G candidate lists laid out [G][B][k] (G = 1: the local list; G > 1: after one all-gather over NVLink)
- * and expands the winners (matching.py:279-316). */
-int gp_topk_merge(gp_handle_t h, int B, int G, const gp_candidates_t* gathered, const gp_matches_t* out, void* stream);
+/* Merges G candidate lists (G = 1: the local list; G > 1: after ONE all-gather over NVLink) into the global top-k
+ * (score descending, then global template id ascending) and expands the winners (matching.py:279-316).
+ * List g of every field starts `rank_stride_bytes * g` bytes after the field pointer (the packed all-gather
+ * buffer); rank_stride_bytes = 0 means each field is a dense [G][B][k][...] array.  If the candidates carry
+ * rel_scale / rel_inplane, the winners' rows are copied to out_rel_scale [B,k,256] / out_rel_inplane [B,k,256,2]. */
+int gp_topk_merge(gp_handle_t h, int B, int G, const gp_candidates_t* gathered, size_t rank_stride_bytes,
+                  const gp_matches_t* out, float* out_rel_scale, float* out_rel_inplane, void* stream);
 /* Single-GPU convenience: gp_sim_candidates into the workspace + gp_topk_merge(G=1) == LocalSimilarity.test. */
 int gp_sim_topk(gp_handle_t h, int B, const gp_matches_t* out, void* stream);
 
