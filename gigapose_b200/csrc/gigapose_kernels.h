@@ -151,4 +151,27 @@ cudaError_t launch_pose_only(int n, int k, int T, const int* q_obj, const float*
                              const long long* id_src, const float* M, const float* tmpl_K, const float* tmpl_M,
                              const float* tmpl_pose, float* poses, cudaStream_t stream);
 
+// ---------------------------------------------------------------- ViT-L/14 (vit_gemm.cu, vit_ops.cu)
+enum GemmMode { GEMM_PLANES = 0, GEMM_PLANES_GELU = 1, GEMM_SCALE_RESIDUAL = 2, GEMM_PATCH_EMBED = 3 };
+struct GemmParams {
+  int M, N, K;                // C[M,N] = A[M,K] W[N,K]^T ; N % 256 == 0, K % 32 == 0
+  int passes;                 // 3 = hi*hi + hi*lo + lo*hi, 1 = hi*hi
+  int mode;                   // GemmMode
+  const float* bias;          // [N]
+  const float* gamma;         // [N]      LayerScale (GEMM_SCALE_RESIDUAL)
+  float* x;                   // fp32 rows (GEMM_SCALE_RESIDUAL: in/out [M,N]; GEMM_PATCH_EMBED: out [imgs*257, N])
+  uint16_t *out_hi, *out_lo;  // bf16 planes [M,N] (GEMM_PLANES*)
+  const float* pos;           // [257,N] positional table (GEMM_PATCH_EMBED)
+  int tokens_per_img, patches_per_img;
+};
+cudaError_t launch_vit_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                            const CUtensorMap& w_lo, const GemmParams& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_split_planes(const float* x, long long rows, int K, int Kpad, uint16_t* hi, uint16_t* lo, cudaStream_t s);
+cudaError_t launch_im2col(const float* img, int b, int Kpad, uint16_t* hi, uint16_t* lo, cudaStream_t s);
+cudaError_t launch_cls_rows(const float* cls, const float* pos, int b, float* x, cudaStream_t s);
+cudaError_t launch_layernorm_planes(const float* x, int M, const float* w, const float* b, float eps, uint16_t* hi,
+                                    uint16_t* lo, cudaStream_t s);
+cudaError_t launch_attention(const uint16_t* qkv_hi, const uint16_t* qkv_lo, uint16_t* out_hi, uint16_t* out_lo, int b,
+                             int passes, cudaStream_t s);
+
 }  // namespace gp

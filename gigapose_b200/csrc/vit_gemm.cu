@@ -1,0 +1,227 @@
+// Linear layers of the DINOv2 ViT-L/14 forward on tcgen05 (row a1 of SURVEY.md §8; the hub module the reference
+// calls at ae_net.py:46 runs these as fp32 cuBLAS GEMMs).
+//
+// C[M,N] = A[M,K] . W[N,K]^T with both operands stored as bf16 hi/lo planes (x = hi + lo to ~2^-17) and accumulated
+// as hi*hi + hi*lo + lo*hi in fp32 TMEM accumulators -- the same fp32-faithful split as the similarity kernel
+// (`passes = 1` = plain bf16).  Persistent CTAs, one 128 x 256 output tile at a time:
+//   warp 0  TMA producer   (A box 128 x 32, W box 256 x 32, SWIZZLE_64B, 4-stage ring)
+//   warp 1  UMMA issuer    (cta_group::1, M=128, N=256, K=16), two TMEM accumulators (2 x 256 columns)
+//   warp 2  TMEM allocator
+//   warps 4-11 epilogue    (TMEM -> registers -> fused bias / GELU / LayerScale + residual / positional table ->
+//                           fp32 rows or bf16 hi/lo planes for the next GEMM), overlapping the next tile's MMAs.
+#include "gigapose_kernels.h"
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace gp {
+
+namespace {
+
+constexpr int kBlockK = 32;
+constexpr int kRowBytes = kBlockK * 2;            // 64 B rows, SWIZZLE_64B
+constexpr int kStages = 4;
+constexpr int kBM = 128, kBN = 256;
+constexpr int kAPlane = kBM * kRowBytes;          // 8 KB
+constexpr int kWPlane = kBN * kRowBytes;          // 16 KB
+constexpr int kStageBytes = 2 * kAPlane + 2 * kWPlane;   // 48 KB
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 4 * 32 + kEpiWarps * 32;
+constexpr uint32_t kIdesc = umma_idesc_f16(kBM, kBN, 1);
+
+struct __align__(8) GemmSmemTail {
+  uint64_t full_bar[kStages];
+  uint64_t empty_bar[kStages];
+  uint64_t tmem_full_bar[2];
+  uint64_t tmem_empty_bar[2];
+  uint32_t tmem_base;
+};
+constexpr int kSmemBytes = 1024 + kStages * kStageBytes + sizeof(GemmSmemTail);
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1)
+vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  GemmSmemTail& tail = *reinterpret_cast<GemmSmemTail*>(smem + kStages * kStageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int passes = p.passes;
+  const int num_m = (p.M + kBM - 1) / kBM, num_n = p.N / kBN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = p.K / kBlockK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&tail.full_bar[s], 1); mbar_init(&tail.empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tail.tmem_full_bar[a], 1); mbar_init(&tail.tmem_empty_bar[a], kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_w_hi);
+    if (passes == 3) { tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_w_lo); }
+  }
+  if (warp == 2) tmem_alloc(&tail.tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tail.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx = (passes == 3 ? 2 : 1) * (kAPlane + kWPlane);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % num_m) * kBM, n0 = (tile / num_m) * kBN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&tail.empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * kStageBytes;
+          mbar_arrive_expect_tx(&tail.full_bar[stage], tx);
+          tma_load_2d(st, &tm_a_hi, &tail.full_bar[stage], kb * kBlockK, m0);
+          tma_load_2d(st + 2 * kAPlane, &tm_w_hi, &tail.full_bar[stage], kb * kBlockK, n0);
+          if (passes == 3) {
+            tma_load_2d(st + 2 * kAPlane + kWPlane, &tm_w_lo, &tail.full_bar[stage], kb * kBlockK, n0);
+            tma_load_2d(st + kAPlane, &tm_a_lo, &tail.full_bar[stage], kb * kBlockK, m0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0, unit = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++unit) {
+        const uint32_t acc = unit & 1u;
+        mbar_wait(&tail.tmem_empty_bar[acc], ((unit >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * 256;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&tail.full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + stage * kStageBytes);
+          const uint32_t a_hi = st, a_lo = st + kAPlane, w_hi = st + 2 * kAPlane, w_lo = st + 2 * kAPlane + kWPlane;
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            if (pass < passes) {
+              const uint32_t a = (pass == 2 ? a_lo : a_hi), w = (pass == 1 ? w_lo : w_hi);
+#pragma unroll
+              for (int k16 = 0; k16 < kBlockK / 16; ++k16)
+                umma_f16(d, umma_desc_kmajor<kRowBytes>(a + k16 * 32), umma_desc_kmajor<kRowBytes>(w + k16 * 32), kIdesc,
+                         (kb | pass | k16) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&tail.empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tail.tmem_full_bar[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int e = warp - 4, q = e & 3, ch = e >> 2;
+    const int r = q * 32 + lane;
+    uint32_t unit = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++unit) {
+      const uint32_t acc = unit & 1u;
+      const int m = (tile % num_m) * kBM + r;
+      const int n0 = (tile / num_m) * kBN + ch * 128;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + ch * 128;
+      mbar_wait(&tail.tmem_full_bar[acc], (unit >> 1) & 1u);
+      tc_fence_after();
+      const bool row_ok = m < p.M;
+      size_t out_row = (size_t)m;
+      const float* pos_row = nullptr;
+      if (p.mode == GEMM_PATCH_EMBED) {                // patch row -> token row (CLS first), + positional table
+        const int img = m / p.patches_per_img, pp = m - img * p.patches_per_img;
+        out_row = (size_t)img * p.tokens_per_img + 1 + pp;
+        pos_row = p.pos + (size_t)(1 + pp) * p.N;
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v32[32];
+        tmem_ld_32x32(taddr + c0, v32);
+        tmem_ld_wait();
+        const int n = n0 + c0;
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(v32[j]) + __ldg(p.bias + n + j);
+          if (p.mode == GEMM_PLANES || p.mode == GEMM_PLANES_GELU) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float a = v[j], b = v[j + 1];
+              if (p.mode == GEMM_PLANES_GELU) { a = gelu_erf(a); b = gelu_erf(b); }
+              const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+              hi[j >> 1] = pack_bf16(ah, bh);
+              lo[j >> 1] = pack_bf16(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
+            }
+            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + out_row * p.N + n);   // uint16_t planes
+            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + out_row * p.N + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+          } else {
+            float4* dst = reinterpret_cast<float4*>(p.x + out_row * p.N + n);
+            if (p.mode == GEMM_SCALE_RESIDUAL) {       // x += gamma * (acc + bias)   (blocks: ls1 / ls2 + residual)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 xr = dst[j];
+                float4 o;
+                o.x = xr.x + __ldg(p.gamma + n + 4 * j + 0) * v[4 * j + 0];
+                o.y = xr.y + __ldg(p.gamma + n + 4 * j + 1) * v[4 * j + 1];
+                o.z = xr.z + __ldg(p.gamma + n + 4 * j + 2) * v[4 * j + 2];
+                o.w = xr.w + __ldg(p.gamma + n + 4 * j + 3) * v[4 * j + 3];
+                dst[j] = o;
+              }
+            } else {                                    // GEMM_PATCH_EMBED
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 o;
+                o.x = v[4 * j + 0] + __ldg(pos_row + n + 4 * j + 0);
+                o.y = v[4 * j + 1] + __ldg(pos_row + n + 4 * j + 1);
+                o.z = v[4 * j + 2] + __ldg(pos_row + n + 4 * j + 2);
+                o.w = v[4 * j + 3] + __ldg(pos_row + n + 4 * j + 3);
+                dst[j] = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail.tmem_empty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+cudaError_t launch_vit_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                            const CUtensorMap& w_lo, const GemmParams& p, int num_sms, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(vit_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (p.M <= 0) return cudaSuccess;
+  if (p.N % kBN != 0 || p.K % kBlockK != 0) return cudaErrorInvalidValue;
+  const int tiles = ((p.M + kBM - 1) / kBM) * (p.N / kBN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  vit_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(a_hi, a_lo, w_hi, w_lo, p);
+  return cudaGetLastError();
+}
+
+}  // namespace gp

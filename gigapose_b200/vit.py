@@ -66,7 +66,6 @@ class DinoVisionTransformer(nn.Module):
         self.patch_embed = _PatchEmbed(embed_dim, patch_size)
         self.blocks = nn.ModuleList([_Block(embed_dim, num_heads, mlp_ratio) for _ in range(depth)])
         self.norm = nn.LayerNorm(embed_dim, eps=1e-6)
-        self._engine = None
         if init_seed is not None:
             self.seeded_init(init_seed)
 
@@ -85,7 +84,6 @@ class DinoVisionTransformer(nn.Module):
                 p.copy_(torch.randn(p.shape, generator=g) / math.sqrt(p[0].numel()))
             else:
                 p.copy_(0.02 * torch.randn(p.shape, generator=g))
-        self._engine = None
 
     def interpolated_pos_embed(self, gh: int, gw: int) -> torch.Tensor:
         """Weight-only: the [1, 1+gh*gw, dim] table upstream rebuilds at every forward (bicubic, offset 0.1)."""

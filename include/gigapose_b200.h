@@ -173,6 +173,27 @@ int gp_sort_and_pose(gp_handle_t h, int B, const float* q_K, const float* q_M, c
                      const float* rel_scale, const float* rel_inplane, const gp_ransac_out_t* r,
                      const gp_predictions_t* out, void* stream);
 
+/* --- row a1: DINOv2 ViT-L/14 patch tokens (AENet.forward_by_chunk, ae_net.py:55-69; hub module un-vendored) ---- */
+typedef struct gp_vit_context* gp_vit_handle_t;
+
+/* Bytes for the packed weights (bf16 hi/lo planes) and for the activation workspace of `max_crops` crops. */
+int gp_vit_query_sizes(int depth, int max_crops, size_t* weight_bytes, size_t* workspace_bytes);
+
+/* `weights`: 4 + 14*depth f32 device pointers in upstream state-dict order --
+ *   patch_embed.proj.weight [1024,3,14,14], patch_embed.proj.bias [1024], cls_token [1024],
+ *   pos table [257,1024] (pos_embed already interpolated to the 16x16 grid: a weight-only computation),
+ *   then per block: norm1.weight, norm1.bias, attn.qkv.weight [3072,1024], attn.qkv.bias, attn.proj.weight [1024,1024],
+ *   attn.proj.bias, ls1.gamma, norm2.weight, norm2.bias, mlp.fc1.weight [4096,1024], mlp.fc1.bias,
+ *   mlp.fc2.weight [1024,4096], mlp.fc2.bias, ls2.gamma.
+ * GEMM weights are packed into `weight_mem` on `stream`; biases / norms / gammas / tables are referenced in place
+ * (the caller keeps them alive).  precision: GP_PRECISION_FP32_SPLIT or GP_PRECISION_BF16. */
+int gp_vit_create(int device, int depth, int max_crops, int precision, const float* const* weights, void* weight_mem,
+                  void* workspace_mem, void* stream, gp_vit_handle_t* out);
+int gp_vit_destroy(gp_vit_handle_t h);
+/* img f32 [b,3,224,224] -> x_prenorm f32 [b,257,1024]: tokens after the last block, before the final norm
+ * (DinoVisionTransformer.forward_features()["x_prenorm"], the tensor ae_net.py:65 slices). */
+int gp_vit_forward(gp_vit_handle_t h, int b, const float* img, float* x_prenorm, void* stream);
+
 /* --- diagnostics ----------------------------------------------------------------------------------------- */
 /* number of kernels this library has launched since load (all handles); used for bench.py's `gpu_launches` */
 uint64_t gp_launch_count(void);

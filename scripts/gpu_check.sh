@@ -4,7 +4,8 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu_info.txt 2>&1
 python - <<'PY' > gpurun_out/collect.txt 2>&1
 import subprocess, sys
-out = subprocess.run([sys.executable, "-m", "pytest", "tests", "-m", "gpu", "--collect-only", "-q"], capture_output=True, text=True).stdout
+import os
+out = subprocess.run([sys.executable, "-m", "pytest", os.environ.get("GPU_TESTS", "tests"), "-m", "gpu", "--collect-only", "-q"], capture_output=True, text=True).stdout
 ids = [l.strip() for l in out.splitlines() if "::" in l]
 print("\n".join(ids))
 PY
