@@ -239,12 +239,13 @@ def run_sharded_bench(args, cfg, config, wl_name, rank, world, device, METRIC, U
                   for k in ("tar_img", "tar_mask", "tar_K", "tar_M"))
         line = {"metric": METRIC, "value": B / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 (a1/a6: fp32 library kernels; a4: bf16x3 split on tcgen05, fp32 accumulate; a5,a7-a9: fp32)",
+                "dtype": "f32 (a1, a4: bf16 hi/lo split x3 on tensor cores with fp32 accumulate = fp32-faithful; a5, a7-a9: fp32; "
+                         "a6: fp32 cuDNN)",
                 "data": "synthetic",
                 "config": dict(config, parallelism=f"template-interleaved bank shards x{world}, crops data-parallel, "
                                                    "1 all-gather of features + 1 all-gather of top-k records per batch",
-                               native_rows=["a3", "a4", "a5", "a7", "a8", "a9", "e"],
-                               library_rows=[f"a1 ViT-L/14 ({vit_engine.BACKEND})", "a6 IST ResNet (cuDNN)"],
+                               native_rows=[f"a1 ViT-L/14 ({vit_engine.BACKEND})", "a2", "a3", "a4", "a5", "a7", "a8", "a9", "e"],
+                               library_rows=["a6 IST ResNet (cuDNN via torch, SURVEY f1 'next')"],
                                planted_view_in_topk=hit),
                 "clocks": clocks.summary(),
                 "e2e": {"value": B / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
