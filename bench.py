@@ -132,43 +132,90 @@ def make_queries(templates: SyntheticTemplates, B, seed=42):
 # clocks sampling during the timed region
 # ----------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock + throttle reasons DURING the timed region through NVML (in-process: a polling `nvidia-smi`
+    subprocess was measured to slow the launching thread by 50 %).  Falls back to one `nvidia-smi` query before and
+    after the region when pynvml is unavailable."""
 
     def __init__(self, index=0):
         self.index, self.samples, self.reasons = index, [], set()
         self.max_mhz = None
         self._stop = threading.Event()
         self._t = None
+        self._nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[index])
+            except Exception:
+                return index
+        return index
+
+    def _sample_nvml(self):
+        nv = self._nv
+        self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        flags = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        for n, bit in flags.items():
+            if r & bit:
+                self.reasons.add(n)
+
+    def _sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                 capture_output=True, text=True, timeout=5).stdout.strip()
+            f = [x.strip() for x in out.split(",")]
+            self.samples.append(float(f[0]))
+            self.max_mhz = float(f[1])
+            for n, v in zip(names, f[2:]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(n)
+        except Exception:
+            pass
 
     def _run(self):
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                f = [x.strip() for x in out.split(",")]
-                self.samples.append(float(f[0]))
-                self.max_mhz = float(f[1])
-                for n, v in zip(names, f[2:]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(n)
+                self._sample_nvml()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        if self._nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        else:
+            self._sample_smi()
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self._t is not None:
+            self._stop.set()
+            self._t.join(timeout=2)
+        else:
+            self._sample_smi()
 
     def summary(self):
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "source": "nvml" if self._nv is not None else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -29,6 +29,8 @@ constexpr int kThreads = 4 * 32 + kEpiWarps * 32;
 constexpr uint32_t kIdesc = umma_idesc_f16(kBM, kBN, 1);
 
 struct __align__(8) GemmSmemTail {
+  float bias_s[2][kBN];                           // per-tile bias / LayerScale columns, double buffered with the accumulator
+  float gamma_s[2][kBN];
   uint64_t full_bar[kStages];
   uint64_t empty_bar[kStages];
   uint64_t tmem_full_bar[2];
@@ -124,14 +126,20 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   } else if (warp >= 4) {
     const int e = warp - 4, q = e & 3, ch = e >> 2;
     const int r = q * 32 + lane;
+    const int etid = e * 32 + lane;
     uint32_t unit = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++unit) {
       const uint32_t acc = unit & 1u;
       const int m = (tile % num_m) * kBM + r;
-      const int n0 = (tile / num_m) * kBN + ch * 128;
+      const int ntile0 = (tile / num_m) * kBN;
+      const int n0 = ntile0 + ch * 128;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + ch * 128;
-      mbar_wait(&tail.tmem_full_bar[acc], (unit >> 1) & 1u);
-      tc_fence_after();
+      // stage the per-column vectors of this tile (256 epilogue threads, one column each)
+      tail.bias_s[acc][etid] = __ldg(p.bias + ntile0 + etid);
+      if (p.mode == GEMM_SCALE_RESIDUAL) tail.gamma_s[acc][etid] = __ldg(p.gamma + ntile0 + etid);
+      named_barrier_sync(1, kEpiWarps * 32);
+      const float* sb = tail.bias_s[acc] + ch * 128;
+      const float* sg = tail.gamma_s[acc] + ch * 128;
       const bool row_ok = m < p.M;
       size_t out_row = (size_t)m;
       const float* pos_row = nullptr;
@@ -140,63 +148,80 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         out_row = (size_t)img * p.tokens_per_img + 1 + pp;
         pos_row = p.pos + (size_t)(1 + pp) * p.N;
       }
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t v32[32];
-        tmem_ld_32x32(taddr + c0, v32);
-        tmem_ld_wait();
+      // residual rows are prefetched before the accumulator is ready (GEMM_SCALE_RESIDUAL reads what it overwrites)
+      mbar_wait(&tail.tmem_full_bar[acc], (unit >> 1) & 1u);
+      tc_fence_after();
+
+      auto process = [&](uint32_t (&v32)[32], int c0) {
+        if (!row_ok) return;
         const int n = n0 + c0;
-        if (row_ok) {
-          float v[32];
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(v32[j]) + __ldg(p.bias + n + j);
-          if (p.mode == GEMM_PLANES || p.mode == GEMM_PLANES_GELU) {
-            uint32_t hi[16], lo[16];
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(v32[j]) + sb[c0 + j];
+        if (p.mode == GEMM_PLANES || p.mode == GEMM_PLANES_GELU) {
+          uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float a = v[j], b = v[j + 1];
-              if (p.mode == GEMM_PLANES_GELU) { a = gelu_erf(a); b = gelu_erf(b); }
-              const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-              hi[j >> 1] = pack_bf16(ah, bh);
-              lo[j >> 1] = pack_bf16(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
+          for (int j = 0; j < 32; j += 2) {
+            float a = v[j], b = v[j + 1];
+            if (p.mode == GEMM_PLANES_GELU) { a = gelu_erf(a); b = gelu_erf(b); }
+            const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+            hi[j >> 1] = pack_bf16(ah, bh);
+            lo[j >> 1] = pack_bf16(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
+          }
+          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + out_row * p.N + n);
+          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + out_row * p.N + n);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          }
+        } else {
+          float4* dst = reinterpret_cast<float4*>(p.x + out_row * p.N + n);
+          if (p.mode == GEMM_SCALE_RESIDUAL) {         // x += gamma * (acc + bias)   (blocks: ls1 / ls2 + residual)
+            float4 xr[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xr[j] = dst[j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 o;
+              o.x = xr[j].x + sg[c0 + 4 * j + 0] * v[4 * j + 0];
+              o.y = xr[j].y + sg[c0 + 4 * j + 1] * v[4 * j + 1];
+              o.z = xr[j].z + sg[c0 + 4 * j + 2] * v[4 * j + 2];
+              o.w = xr[j].w + sg[c0 + 4 * j + 3] * v[4 * j + 3];
+              dst[j] = o;
             }
-            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + out_row * p.N + n);   // uint16_t planes
-            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + out_row * p.N + n);
+          } else {                                      // GEMM_PATCH_EMBED
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-              dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-            }
-          } else {
-            float4* dst = reinterpret_cast<float4*>(p.x + out_row * p.N + n);
-            if (p.mode == GEMM_SCALE_RESIDUAL) {       // x += gamma * (acc + bias)   (blocks: ls1 / ls2 + residual)
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 xr = dst[j];
-                float4 o;
-                o.x = xr.x + __ldg(p.gamma + n + 4 * j + 0) * v[4 * j + 0];
-                o.y = xr.y + __ldg(p.gamma + n + 4 * j + 1) * v[4 * j + 1];
-                o.z = xr.z + __ldg(p.gamma + n + 4 * j + 2) * v[4 * j + 2];
-                o.w = xr.w + __ldg(p.gamma + n + 4 * j + 3) * v[4 * j + 3];
-                dst[j] = o;
-              }
-            } else {                                    // GEMM_PATCH_EMBED
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 o;
-                o.x = v[4 * j + 0] + __ldg(pos_row + n + 4 * j + 0);
-                o.y = v[4 * j + 1] + __ldg(pos_row + n + 4 * j + 1);
-                o.z = v[4 * j + 2] + __ldg(pos_row + n + 4 * j + 2);
-                o.w = v[4 * j + 3] + __ldg(pos_row + n + 4 * j + 3);
-                dst[j] = o;
-              }
+            for (int j = 0; j < 8; ++j) {
+              float4 o;
+              o.x = v[4 * j + 0] + __ldg(pos_row + n + 4 * j + 0);
+              o.y = v[4 * j + 1] + __ldg(pos_row + n + 4 * j + 1);
+              o.z = v[4 * j + 2] + __ldg(pos_row + n + 4 * j + 2);
+              o.w = v[4 * j + 3] + __ldg(pos_row + n + 4 * j + 3);
+              dst[j] = o;
             }
           }
         }
-      }
+      };
+
+      // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is processed
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(taddr, va);
+      tmem_ld_wait_for(va);
+      tmem_ld_32x32(taddr + 32, vb);
+      process(va, 0);
+      tmem_ld_wait_for(vb);
+      tmem_ld_32x32(taddr + 64, va);
+      process(vb, 32);
+      tmem_ld_wait_for(va);
+      tmem_ld_32x32(taddr + 96, vb);
+      process(va, 64);
+      tmem_ld_wait_for(vb);
+      // accumulator fully read -> hand it back to the UMMA warp before the last chunk's math / stores
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail.tmem_empty_bar[acc]);
+      process(vb, 96);
     }
   }
 

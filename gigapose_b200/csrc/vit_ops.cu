@@ -3,7 +3,7 @@
 // fp32 -> hi/lo plane split used to pack weights.
 //
 // Attention: one CTA per (crop, head); all 257 keys / values of the head are staged once in shared memory as bf16
-// hi/lo planes (XOR-swizzled 16-byte chunks, conflict-free ldmatrix) and six warps walk the 17 query row groups with
+// hi/lo planes (XOR-swizzled 16-byte chunks, conflict-free ldmatrix) and nine warps walk the 17 query row groups with
 // an online softmax.  The two products use the same fp32-faithful split as the GEMMs:
 //   S = Qh.Kh^T + Qh.Kl^T + Ql.Kh^T,   O = Ph.Vh + Ph.Vl + Pl.Vh      (mma.sync m16n8k16 bf16, fp32 accumulate).
 // At 257 x 64 per head the problem is far below one tcgen05 tile per CTA pair and is 4 % of the ViT FLOPs; the
@@ -110,7 +110,7 @@ layernorm_planes_kernel(const float* __restrict__ x, int M, const float* __restr
 // ---------------------------------------------------------------- attention
 constexpr int kKeyPad = 320;                       // 257 keys padded to 5 tiles of 64
 constexpr int kQGroups = 17;                       // ceil(257 / 16) query row groups
-constexpr int kAttnWarps = 6;
+constexpr int kAttnWarps = 9;                      // 17 row groups -> 9 + 8
 constexpr int kPlane = kKeyPad * kHd * 2;          // 40 KB: one bf16 plane of K or V (rows of 128 B)
 constexpr int kAttnSmem = 4 * kPlane + 2 * (kAttnWarps * 16 * kHd * 2);   // K hi/lo, V hi/lo + per-warp Q hi/lo
 
@@ -173,8 +173,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* 
   __syncthreads();
 
   const int g = lane >> 2, t = lane & 3;
-  for (int qg = warp; qg < kQGroups + (kAttnWarps - kQGroups % kAttnWarps) % kAttnWarps; qg += kAttnWarps) {
-    if (qg >= kQGroups) break;
+  for (int qg = warp; qg < kQGroups; qg += kAttnWarps) {
     const int q0 = qg * 16;
     // stage this warp's 16 query rows (hi/lo)
     for (int i = lane; i < 16 * 8; i += 32) {

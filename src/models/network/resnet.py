@@ -6,8 +6,16 @@ torch) until its native implicit-GEMM version lands; it is listed as `library` i
 the reference state dict (`conv1, bn1, layer{1..4}.{0,1}.{conv1,conv2,bn1,bn2,downsample.{0,1}}, layer4_outconv`).
 The optional attention blocks of the reference (n_heads > 0) are dead under the shipped config and not provided.
 """
+import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+
+def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d):
+    """Inference-time BatchNorm folding: conv(x) * g + h  with g = gamma / sqrt(var + eps), h = beta - mean * g."""
+    g = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    w = (conv.weight * g.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
+    return w, (bn.bias - bn.running_mean * g).contiguous()
 
 
 class BasicBlock(nn.Module):
@@ -51,6 +59,38 @@ class ResNet(nn.Module):
     def forward(self, x):
         # the reference resizes 224 -> 256 with align_corners=True before the trunk (resnet.py:365-368)
         x = F.interpolate(x, (self.input_size, self.input_size), mode="bilinear", align_corners=True)
+        if not self.training and x.is_cuda and not torch.is_grad_enabled():
+            return self._forward_folded(x)
         x = F.relu(self.bn1(self.conv1(x)))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.layer4_outconv(x)
+
+    # ---- inference path: BatchNorm folded into the convolutions, NHWC end to end (no layout-conversion kernels)
+    def _folded_params(self):
+        key = sum(int(p._version) for p in self.parameters()) + sum(int(b._version) for b in self.buffers())
+        cache = getattr(self, "_folded", None)
+        if cache is not None and cache[0] == key:
+            return cache[1]
+        with torch.no_grad():
+            params = {"stem": _fold(self.conv1, self.bn1), "blocks": [],
+                      "out": self.layer4_outconv.weight.contiguous(memory_format=torch.channels_last)}
+            for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+                for blk in layer:
+                    ds = _fold(blk.downsample[0], blk.downsample[1]) if blk.downsample is not None else None
+                    params["blocks"].append((_fold(blk.conv1, blk.bn1), _fold(blk.conv2, blk.bn2), ds,
+                                             blk.conv1.stride))
+        object.__setattr__(self, "_folded", (key, params))
+        return params
+
+    def _forward_folded(self, x):
+        p = self._folded_params()
+        x = x.contiguous(memory_format=torch.channels_last)
+        w, b = p["stem"]
+        x = F.relu_(F.conv2d(x, w, b, stride=2, padding=3))
+        for (w1, b1), (w2, b2), ds, stride in p["blocks"]:
+            y = F.relu_(F.conv2d(x, w1, b1, stride=stride, padding=1))
+            y = F.conv2d(y, w2, b2, stride=1, padding=1)
+            if ds is not None:
+                x = F.conv2d(x, ds[0], ds[1], stride=stride)
+            x = F.relu_(x + y)
+        return F.conv2d(x, p["out"]).contiguous()
