@@ -39,6 +39,19 @@ struct __align__(8) GemmSmemTail {
 };
 constexpr int kSmemBytes = 1024 + kStages * kStageBytes + sizeof(GemmSmemTail);
 
+// Grouped rasterisation: 16 m-tiles x all n-tiles per group, m fastest inside a group.  With plain m-fastest order all
+// 148 CTAs stream the same 256-row weight tile at the same moment and serialise on its L2 lines; in a group every
+// weight tile is shared by <= 16 CTAs and every activation tile by <= num_n CTAs.
+constexpr int kGroupM = 16;
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_tile, int& n_tile) {
+  const int per_group = kGroupM * num_n;
+  const int g = tile / per_group, idx = tile - g * per_group;
+  const int m_first = g * kGroupM;
+  const int gm = min(kGroupM, num_m - m_first);
+  n_tile = idx / gm;
+  m_tile = m_first + (idx - n_tile * gm);
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
@@ -79,7 +92,9 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       int stage = 0; uint32_t phase = 0;
       const uint32_t tx = (passes == 3 ? 2 : 1) * (kAPlane + kWPlane);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % num_m) * kBM, n0 = (tile / num_m) * kBN;
+        int mt, nt;
+        tile_coords(tile, num_m, num_n, mt, nt);
+        const int m0 = mt * kBM, n0 = nt * kBN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&tail.empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * kStageBytes;
@@ -130,8 +145,10 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     uint32_t unit = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++unit) {
       const uint32_t acc = unit & 1u;
-      const int m = (tile % num_m) * kBM + r;
-      const int ntile0 = (tile / num_m) * kBN;
+      int mt, nt;
+      tile_coords(tile, num_m, num_n, mt, nt);
+      const int m = mt * kBM + r;
+      const int ntile0 = nt * kBN;
       const int n0 = ntile0 + ch * 128;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + ch * 128;
       // stage the per-column vectors of this tile (256 epilogue threads, one column each)
