@@ -333,6 +333,12 @@ def main():
     launches = (eng.launch_count() - l0) // args.steps
     value = cfg["B"] / (ms / 1e3)
 
+    # per-stage CUDA-event times of one extra resident step (diagnostic, outside the timed region)
+    model.profile_stages = True
+    step_resident()
+    model.profile_stages = False
+    stage_ms = {k: round(v, 3) for k, v in model.stage_ms.items()}
+
     if args.profile_range:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
@@ -366,8 +372,17 @@ def main():
     sim_ms = eng.time_sim_kernel(iters=20)
     flops = eng.sim_flops(cfg["B"])
     achieved = flops / (sim_ms / 1e3) / 1e12
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "sim_search_traffic.json")))
+        if tr.get("workload") == wl_name:
+            traffic = tr["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": "sim_search_kernel", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "traffic": None, "ms_per_launch": sim_ms,
+                "frac": achieved / peak_tf, "traffic": traffic, "ms_per_launch": sim_ms,
+                "executed_tflops": 3 * achieved, "executed_frac_of_peak": 3 * achieved / peak_tf,
+                "algorithmic_bytes_per_launch": cfg["O"] * cfg["T"] * 256 * 1024 * 4 + cfg["B"] * 256 * 1024 * 4,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1590 (B200_PROFILING.md)",
                 "note": "algorithmic FLOPs = 2*T*P^2*C per detection; the fp32-faithful mode executes 3 bf16 tensor passes "
                         "per algorithmic FLOP, so frac <= 1/3 by construction"}
@@ -383,7 +398,7 @@ def main():
             "clocks": clocks.summary(),
             "e2e": {"value": cfg["B"] / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
-            "gpu_launches": int(launches), "roofline": roofline}
+            "gpu_launches": int(launches), "roofline": roofline, "stage_ms": stage_ms}
     if not args.no_cpu_baseline:
         v, info = cpu_reference_rate(cfg, sample_dets=8, reps=2)
         line["cpu_baseline"] = dict(value=v, unit=UNIT, **info)

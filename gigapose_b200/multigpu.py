@@ -238,7 +238,8 @@ def run_sharded_bench(args, cfg, config, wl_name, rank, world, device, METRIC, U
         h2d = sum(batch_host._tensors[k].numel() * batch_host._tensors[k].element_size()
                   for k in ("tar_img", "tar_mask", "tar_K", "tar_M"))
         line = {"metric": METRIC, "value": B / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong" if wl_name == "c2" else "weak", "vs_baseline": None,
                 "dtype": "f32 (a1, a4: bf16 hi/lo split x3 on tensor cores with fp32 accumulate = fp32-faithful; a5, a7-a9: fp32; "
                          "a6: fp32 cuDNN)",
                 "data": "synthetic",

@@ -49,6 +49,8 @@ class GigaPose(LightningModule):
         self.test_dataset_name = None
         self.max_dets_per_call = int(kwargs.get("max_dets_per_call", 128))
         self.last_times = {}
+        self.profile_stages = False          # bench.py --stage-times: CUDA events between the stages of retrieve()
+        self.stage_ms = {}
 
     # ------------------------------------------------------------------ out of scope: training
     def training_step(self, *a, **k):
@@ -137,18 +139,38 @@ class GigaPose(LightningModule):
         B = tar_img.shape[0]
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         ev[0].record()
+        marks = []
+
+        def mark(name):
+            if self.profile_stages:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+
         for b0 in range(0, B, eng.max_batch):
             sl = slice(b0, min(B, b0 + eng.max_batch))
+            mark("start")
             tokens = self.ae_net.patch_tokens(tar_img[sl])
+            mark("a1_vit")
             eng.set_queries(tokens, tar_mask[sl], q_obj[sl], norm_passes=1)
             m = eng.sim_topk()
+            mark("a3_a4_similarity_topk")
             tar_ist = self.ist_net.forward_by_chunk(tar_img[sl])                 # once, not k times
+            mark("a6_ist_backbone")
             rel_scale, rel_inplane = eng.ist_mlp(tar_ist, m)
+            mark("a5_ist_mlp")
             if b0 == 0:
                 ev[1].record()
             r = eng.ransac(m, rel_scale, rel_inplane)
             outs.append(eng.sort_and_pose(tar_K[sl], tar_M[sl], m, rel_scale, rel_inplane, r))
+            mark("a7_a8_a9_ransac_sort_pose")
         ev[2].record()
+        if self.profile_stages:
+            torch.cuda.synchronize(device)
+            self.stage_ms = {}
+            for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+                if n1 != "start":
+                    self.stage_ms[n1] = self.stage_ms.get(n1, 0.0) + e0.elapsed_time(e1)
         out = outs[0] if len(outs) == 1 else {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
         self._events = ev
         return tc.PandasTensorCollection(infos=batch.infos, **out)
