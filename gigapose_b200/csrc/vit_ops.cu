@@ -206,23 +206,34 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* 
       float s[8][4];
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
-      // S = Q K^T over d: B operand = K[key][d], 8 x 8 blocks, non-transposed ldmatrix
+      // S = Q K^T over d: B operand = K[key][d], 8 x 8 blocks, non-transposed ldmatrix.  The three split passes are
+      // issued tile-major (8 independent accumulators between two MMAs on the same tile) to hide the MMA latency.
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
+        uint32_t bh[4][4], bl[4][4];
 #pragma unroll
         for (int np = 0; np < 4; ++np) {               // pairs of 8-key n-tiles
           const int row = key0 + np * 16 + (lane >> 4) * 8 + (lane & 7);
           const int chunk = ks * 2 + ((lane >> 3) & 1);
-          uint32_t bh0, bh1, bh2, bh3, bl0, bl1, bl2, bl3;
-          ldsm_x4((uint32_t)__cvta_generic_to_shared(sKh + swz(row, chunk)), bh0, bh1, bh2, bh3);
-          mma_bf16(s[2 * np], qh[ks], bh0, bh1);
-          mma_bf16(s[2 * np + 1], qh[ks], bh2, bh3);
-          if (passes == 3) {
-            ldsm_x4((uint32_t)__cvta_generic_to_shared(sKl + swz(row, chunk)), bl0, bl1, bl2, bl3);
-            mma_bf16(s[2 * np], qh[ks], bl0, bl1);
-            mma_bf16(s[2 * np + 1], qh[ks], bl2, bl3);
-            mma_bf16(s[2 * np], ql[ks], bh0, bh1);
-            mma_bf16(s[2 * np + 1], ql[ks], bh2, bh3);
+          ldsm_x4((uint32_t)__cvta_generic_to_shared(sKh + swz(row, chunk)), bh[np][0], bh[np][1], bh[np][2], bh[np][3]);
+          if (passes == 3)
+            ldsm_x4((uint32_t)__cvta_generic_to_shared(sKl + swz(row, chunk)), bl[np][0], bl[np][1], bl[np][2], bl[np][3]);
+        }
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          mma_bf16(s[2 * np], qh[ks], bh[np][0], bh[np][1]);
+          mma_bf16(s[2 * np + 1], qh[ks], bh[np][2], bh[np][3]);
+        }
+        if (passes == 3) {
+#pragma unroll
+          for (int np = 0; np < 4; ++np) {
+            mma_bf16(s[2 * np], qh[ks], bl[np][0], bl[np][1]);
+            mma_bf16(s[2 * np + 1], qh[ks], bl[np][2], bl[np][3]);
+          }
+#pragma unroll
+          for (int np = 0; np < 4; ++np) {
+            mma_bf16(s[2 * np], ql[ks], bh[np][0], bh[np][1]);
+            mma_bf16(s[2 * np + 1], ql[ks], bh[np][2], bh[np][3]);
           }
         }
       }
@@ -261,20 +272,30 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* 
         split2(s[2 * ks][2], s[2 * ks][3], ph[1], pl[1]);
         split2(s[2 * ks + 1][0], s[2 * ks + 1][1], ph[2], pl[2]);
         split2(s[2 * ks + 1][2], s[2 * ks + 1][3], ph[3], pl[3]);
+        uint32_t vh[4][4], vl[4][4];
 #pragma unroll
         for (int np = 0; np < 4; ++np) {               // pairs of 8-wide d n-tiles
           const int row = key0 + ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
           const int chunk = np * 2 + (lane >> 4);
-          uint32_t vh0, vh1, vh2, vh3, vl0, vl1, vl2, vl3;
-          ldsm_x4_t((uint32_t)__cvta_generic_to_shared(sVh + swz(row, chunk)), vh0, vh1, vh2, vh3);
-          mma_bf16(o[2 * np], ph, vh0, vh1);
-          mma_bf16(o[2 * np + 1], ph, vh2, vh3);
-          if (passes == 3) {
-            ldsm_x4_t((uint32_t)__cvta_generic_to_shared(sVl + swz(row, chunk)), vl0, vl1, vl2, vl3);
-            mma_bf16(o[2 * np], ph, vl0, vl1);
-            mma_bf16(o[2 * np + 1], ph, vl2, vl3);
-            mma_bf16(o[2 * np], pl, vh0, vh1);
-            mma_bf16(o[2 * np + 1], pl, vh2, vh3);
+          ldsm_x4_t((uint32_t)__cvta_generic_to_shared(sVh + swz(row, chunk)), vh[np][0], vh[np][1], vh[np][2], vh[np][3]);
+          if (passes == 3)
+            ldsm_x4_t((uint32_t)__cvta_generic_to_shared(sVl + swz(row, chunk)), vl[np][0], vl[np][1], vl[np][2], vl[np][3]);
+        }
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          mma_bf16(o[2 * np], ph, vh[np][0], vh[np][1]);
+          mma_bf16(o[2 * np + 1], ph, vh[np][2], vh[np][3]);
+        }
+        if (passes == 3) {
+#pragma unroll
+          for (int np = 0; np < 4; ++np) {
+            mma_bf16(o[2 * np], ph, vl[np][0], vl[np][1]);
+            mma_bf16(o[2 * np + 1], ph, vl[np][2], vl[np][3]);
+          }
+#pragma unroll
+          for (int np = 0; np < 4; ++np) {
+            mma_bf16(o[2 * np], pl, vh[np][0], vh[np][1]);
+            mma_bf16(o[2 * np + 1], pl, vh[np][2], vh[np][3]);
           }
         }
       }
