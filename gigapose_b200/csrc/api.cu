@@ -105,6 +105,22 @@ int gp_internal_make_map(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t co
   return GP_OK;
 }
 
+// generic 2-D bf16 plane map with explicit box and swizzle (swizzle_bytes: 64 or 128 = box_cols * 2)
+int gp_internal_make_map_ex(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows,
+                            int swizzle_bytes) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(GP_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from this driver");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(uint16_t)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return GP_OK;
+}
+
 namespace {
 
 struct Bank {

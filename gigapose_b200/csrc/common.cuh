@@ -121,12 +121,25 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand (rows = K index, 64 contiguous MN elements = one 128-byte SWIZZLE_128B row per K index, i.e. a
+// [K][64] row-major bf16 tile as TMA delivers it): groups of 8 K-rows are SBO = 1024 B apart; LBO (stride between
+// 64-element MN blocks) is unused for N = 64.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= 1ull << 16;                                     // LBO (unused, N == one swizzle atom)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;         // SBO: 8 K-rows x 128 B
+  d |= 1ull << 46;
+  d |= 2ull << 61;                                     // SWIZZLE_128B
+  return d;
+}
+
 // Instruction descriptor for kind::f16: D=f32, A/B = bf16 (1) or f16 (0), both K-major, M x N tile.
-__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int ab_format /*0=f16,1=bf16*/) {
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int ab_format /*0=f16,1=bf16*/, int b_mn_major = 0) {
   return (1u << 4)                                     // c_format = F32
          | (static_cast<uint32_t>(ab_format) << 7)     // a_format
          | (static_cast<uint32_t>(ab_format) << 10)    // b_format
-         | (0u << 15) | (0u << 16)                     // A, B K-major
+         | (0u << 15) | (static_cast<uint32_t>(b_mn_major) << 16)   // A K-major; B K-major (0) or MN-major (1)
          | (static_cast<uint32_t>(N >> 3) << 17)
          | (static_cast<uint32_t>(M >> 4) << 24);
 }
@@ -138,6 +151,15 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// same with the A operand read from TMEM (bf16 pairs packed in 32-bit columns, lane = row)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // mbarrier arrive once all previously issued UMMAs of this thread have completed
@@ -170,6 +192,16 @@ __device__ __forceinline__ void tmem_ld_wait_for(uint32_t (&r)[32]) {
                :
                : "memory");
 }
+
+// registers -> TMEM: 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void named_barrier_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -1,0 +1,243 @@
+// Multi-head self-attention of the ViT-L/14 forward on TMA + tcgen05 (row a1; 257 tokens, 16 heads x 64).
+//
+// One CTA per (crop, head).  K and V of the head (272 key rows: 257 + padding) are TMA-staged once into shared
+// memory as bf16 hi/lo planes (SWIZZLE_128B, 128-byte rows); the 257 query rows go through in three 128-row tiles:
+//   S = Q K^T          tcgen05.mma SS, M=128, N=256+16, K=64      (A = Q tile, B = K, both K-major)   -> TMEM [0,272)
+//   softmax            128 threads, one query row each: tcgen05.ld S, fp32 max / expf / sum; P is written back to TMEM
+//                      as packed bf16 pairs (hi over the S columns already consumed, lo next to it)
+//   O = P V            tcgen05.mma TS, M=128, N=64, K=272          (A = P from TMEM, B = V as MN-major operand)
+//   epilogue           tcgen05.ld O, divide by the row sum, store bf16 hi/lo planes (A operand of the proj GEMM)
+// Both products use the fp32-faithful split: S = Qh Kh + Qh Kl + Ql Kh, O = Ph Vh + Ph Vl + Pl Vh.
+// Warp roles: warp 0 TMA producer (+ TMEM alloc), warp 1 UMMA issuer, warps 2-5 softmax / epilogue.
+#include "gigapose_kernels.h"
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace gp {
+
+namespace {
+
+constexpr int kTok = 257, kDim = 1024, kHeads = 16, kHd = 64;
+constexpr int kKeys = 272;                         // 17 x 16
+constexpr int kRow = 128;                          // bytes per smem row (64 bf16) = SWIZZLE_128B span
+constexpr int kKVPlane = kKeys * kRow;             // 34 KB
+constexpr int kQPlane = 128 * kRow;                // 16 KB
+constexpr int kQTiles = 3;                         // ceil(257 / 128)
+constexpr int kThreads = 6 * 32;
+// TMEM columns: S [0,288) (the MMAs write [0,272); P_hi later overwrites [0,144)), P_lo [288,432), O [432,496)
+constexpr uint32_t kColS = 0, kColPlo = 288, kColO = 432;
+constexpr uint32_t kIdescS256 = umma_idesc_f16(128, 256, 1);
+constexpr uint32_t kIdescS16 = umma_idesc_f16(128, 16, 1);
+constexpr uint32_t kIdescPV = umma_idesc_f16(128, 64, 1, /*B MN-major*/ 1);
+
+struct __align__(8) AttnTail {
+  uint64_t kv_full, q_full[2], q_empty[2], s_full, p_ready, o_full;
+  uint32_t tmem_base;
+};
+constexpr int kSmem = 1024 + 4 * kKVPlane + 4 * kQPlane + sizeof(AttnTail);
+
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_constant__ CUtensorMap tm_lo_128,
+                    const __grid_constant__ CUtensorMap tm_hi_16, const __grid_constant__ CUtensorMap tm_lo_16,
+                    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int passes) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sK[2] = {smem, smem + kKVPlane};                                   // hi, lo
+  uint8_t* sV[2] = {smem + 2 * kKVPlane, smem + 3 * kKVPlane};
+  uint8_t* sQ = smem + 4 * kKVPlane;                                          // [buf][hi|lo]
+  AttnTail& tail = *reinterpret_cast<AttnTail*>(smem + 4 * kKVPlane + 4 * kQPlane);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int img = blockIdx.x / kHeads, head = blockIdx.x % kHeads;
+  const int row0 = img * kTok;                       // first token row of this crop in the [M, 3072] planes
+  const int col_q = head * kHd, col_k = kDim + head * kHd, col_v = 2 * kDim + head * kHd;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&tail.kv_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tail.q_full[i], 1); mbar_init(&tail.q_empty[i], 1); }
+    mbar_init(&tail.s_full, 1);
+    mbar_init(&tail.p_ready, 4);
+    mbar_init(&tail.o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tail.tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tail.tmem_base;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      const int np = passes == 3 ? 2 : 1;
+      mbar_arrive_expect_tx(&tail.kv_full, (uint32_t)(2 * np * kKVPlane));
+      for (int pl = 0; pl < np; ++pl) {
+        const CUtensorMap* m128 = pl ? &tm_lo_128 : &tm_hi_128;
+        const CUtensorMap* m16 = pl ? &tm_lo_16 : &tm_hi_16;
+        tma_load_2d(sK[pl], m128, &tail.kv_full, col_k, row0);
+        tma_load_2d(sK[pl] + 128 * kRow, m128, &tail.kv_full, col_k, row0 + 128);
+        tma_load_2d(sK[pl] + 256 * kRow, m16, &tail.kv_full, col_k, row0 + 256);
+        tma_load_2d(sV[pl], m128, &tail.kv_full, col_v, row0);
+        tma_load_2d(sV[pl] + 128 * kRow, m128, &tail.kv_full, col_v, row0 + 128);
+        tma_load_2d(sV[pl] + 256 * kRow, m16, &tail.kv_full, col_v, row0 + 256);
+      }
+      for (int qt = 0; qt < kQTiles; ++qt) {
+        const int buf = qt & 1;
+        mbar_wait(&tail.q_empty[buf], ((qt >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&tail.q_full[buf], (uint32_t)(np * kQPlane));
+        tma_load_2d(sQ + (buf * 2 + 0) * kQPlane, &tm_hi_128, &tail.q_full[buf], col_q, row0 + qt * 128);
+        if (np == 2) tma_load_2d(sQ + (buf * 2 + 1) * kQPlane, &tm_lo_128, &tail.q_full[buf], col_q, row0 + qt * 128);
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== UMMA issuer ==============================
+    if (lane == 0) {
+      mbar_wait(&tail.kv_full, 0);
+      tc_fence_after();
+      const uint32_t kh = smem_u32(sK[0]), kl = smem_u32(sK[1]), vh = smem_u32(sV[0]), vl = smem_u32(sV[1]);
+      for (int qt = 0; qt < kQTiles; ++qt) {
+        const int buf = qt & 1;
+        mbar_wait(&tail.q_full[buf], (qt >> 1) & 1);
+        tc_fence_after();
+        const uint32_t qh = smem_u32(sQ + (buf * 2 + 0) * kQPlane), ql = smem_u32(sQ + (buf * 2 + 1) * kQPlane);
+        // S = Q K^T : keys [0,256) and [256,272)
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          if (pass < passes) {
+            const uint32_t a = pass == 2 ? ql : qh, b = pass == 1 ? kl : kh;
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16) {
+              const uint32_t acc = (pass | k16) != 0 ? 1u : 0u;
+              umma_f16(tmem + kColS, umma_desc_kmajor<kRow>(a + k16 * 32), umma_desc_kmajor<kRow>(b + k16 * 32), kIdescS256, acc);
+              umma_f16(tmem + kColS + 256, umma_desc_kmajor<kRow>(a + k16 * 32),
+                       umma_desc_kmajor<kRow>(b + 256 * kRow + k16 * 32), kIdescS16, acc);
+            }
+          }
+        }
+        umma_commit(&tail.q_empty[buf]);               // Q buffer free once these MMAs retire
+        umma_commit(&tail.s_full);
+        // O = P V once the softmax warps have written P
+        mbar_wait(&tail.p_ready, qt & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < kKeys / 16; ++j) {         // 17 key steps
+          const uint32_t ph = tmem + kColS + 8 * j, pl = tmem + kColPlo + 8 * j;
+          const uint64_t dvh = umma_desc_mnmajor_sw128(vh + j * 16 * kRow), dvl = umma_desc_mnmajor_sw128(vl + j * 16 * kRow);
+          umma_f16_ts(tmem + kColO, ph, dvh, kIdescPV, j != 0 ? 1u : 0u);
+          if (passes == 3) {
+            umma_f16_ts(tmem + kColO, ph, dvl, kIdescPV, 1u);
+            umma_f16_ts(tmem + kColO, pl, dvh, kIdescPV, 1u);
+          }
+        }
+        umma_commit(&tail.o_full);
+      }
+    }
+  } else {
+    // ============================== softmax + epilogue (warps 2-5) ==============================
+    const int quarter = warp & 3;                      // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;                 // query row inside the tile
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    for (int qt = 0; qt < kQTiles; ++qt) {
+      const int tok = qt * 128 + r;
+      const bool row_ok = tok < kTok;
+      mbar_wait(&tail.s_full, qt & 1);
+      tc_fence_after();
+      // pass 1: row maximum of the scaled logits over the 257 real keys (9 chunks of 32 columns; columns >= 257 are
+      // padding keys / never-written TMEM and are masked)
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 9; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem + lane_base + kColS + 32 * c, v);
+        tmem_ld_wait_for(v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (32 * c + j < kTok) mx = fmaxf(mx, __uint_as_float(v[j]) * 0.125f);
+      }
+      // pass 2: p = exp(s - max); P goes back to TMEM as packed bf16 pairs (hi over S columns already consumed,
+      // lo next to S); row sum in fp32.  The 1/sqrt(64) scale is an exact power of two.
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 9; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem + lane_base + kColS + 32 * c, v);
+        tmem_ld_wait_for(v);
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int ka = 32 * c + 2 * j, kb = ka + 1;
+          const float pa = ka < kTok ? expf(__uint_as_float(v[2 * j]) * 0.125f - mx) : 0.f;
+          const float pb = kb < kTok ? expf(__uint_as_float(v[2 * j + 1]) * 0.125f - mx) : 0.f;
+          sum += pa + pb;
+          const __nv_bfloat16 ah = __float2bfloat16_rn(pa), bh = __float2bfloat16_rn(pb);
+          hi[j] = pack2(ah, bh);
+          lo[j] = pack2(__float2bfloat16_rn(pa - __bfloat162float(ah)), __float2bfloat16_rn(pb - __bfloat162float(bh)));
+        }
+        tmem_st_32x16(tmem + lane_base + kColS + 16 * c, hi);       // columns [16c,16c+16) < 32c+32: already read
+        tmem_st_32x16(tmem + lane_base + kColPlo + 16 * c, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail.p_ready);
+      // epilogue: O / sum -> bf16 hi/lo planes
+      mbar_wait(&tail.o_full, qt & 1);
+      tc_fence_after();
+      const float inv = 1.0f / sum;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem + lane_base + kColO + 32 * c, v);
+        tmem_ld_wait_for(v);
+        if (row_ok) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = __uint_as_float(v[2 * j]) * inv, b = __uint_as_float(v[2 * j + 1]) * inv;
+            const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+            hi[j] = pack2(ah, bh);
+            lo[j] = pack2(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
+          }
+          const size_t o = (size_t)(row0 + tok) * kDim + head * kHd + 32 * c;
+          uint4* dh = reinterpret_cast<uint4*>(out_hi + o);
+          uint4* dl = reinterpret_cast<uint4*>(out_lo + o);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          }
+        }
+      }
+      tc_fence_before();                               // O / S reads done before the next tile's MMAs overwrite them
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+cudaError_t launch_attention_tc(const CUtensorMap& hi128, const CUtensorMap& lo128, const CUtensorMap& hi16,
+                                const CUtensorMap& lo16, uint16_t* out_hi, uint16_t* out_lo, int b, int passes,
+                                cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (b <= 0) return cudaSuccess;
+  attention_tc_kernel<<<b * kHeads, kThreads, kSmem, s>>>(hi128, lo128, hi16, lo16, reinterpret_cast<__nv_bfloat16*>(out_hi),
+                                                         reinterpret_cast<__nv_bfloat16*>(out_lo), passes);
+  return cudaGetLastError();
+}
+
+}  // namespace gp

@@ -85,12 +85,22 @@ class ResNet(nn.Module):
     def _forward_folded(self, x):
         p = self._folded_params()
         x = x.contiguous(memory_format=torch.channels_last)
+        fused = x.is_cuda and hasattr(torch, "cudnn_convolution_relu")
+        one = (1, 1)
+
+        def conv_relu(inp, w, b, stride, pad):
+            if fused:     # cuDNN's fused conv + bias + ReLU (no separate elementwise kernels)
+                return torch.cudnn_convolution_relu(inp, w, b, stride, (pad, pad), one, 1)
+            return F.relu_(F.conv2d(inp, w, b, stride=stride, padding=pad))
+
         w, b = p["stem"]
-        x = F.relu_(F.conv2d(x, w, b, stride=2, padding=3))
+        x = conv_relu(x, w, b, (2, 2), 3)
         for (w1, b1), (w2, b2), ds, stride in p["blocks"]:
-            y = F.relu_(F.conv2d(x, w1, b1, stride=stride, padding=1))
-            y = F.conv2d(y, w2, b2, stride=1, padding=1)
+            y = conv_relu(x, w1, b1, tuple(stride), 1)
             if ds is not None:
                 x = F.conv2d(x, ds[0], ds[1], stride=stride)
-            x = F.relu_(x + y)
+            if fused:     # relu(conv(y) + bias + 1.0 * shortcut)
+                x = torch.cudnn_convolution_add_relu(y, w2, x, 1.0, b2, one, (1, 1), one, 1)
+            else:
+                x = F.relu_(x + F.conv2d(y, w2, b2, stride=1, padding=1))
         return F.conv2d(x, p["out"]).contiguous()

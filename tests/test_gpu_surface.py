@@ -126,3 +126,23 @@ def test_gigapose_module_end_to_end_small():
     # oracle for the matching stage on the GPU-computed features of the same crops
     eng = model.engines["synthetic"]
     assert eng.launch_count() > 0
+
+
+def test_ist_backbone_matches_oracle(golden_dir):
+    """Row a6 (library stage: cuDNN through torch, BN folded, NHWC).  cuDNN convolutions run in TF32 by torch's default
+    (the reference's own GPU behaviour), hence the 3e-3 relative tolerance against the fp32 CPU oracle."""
+    import os
+    import numpy as np
+    from src.models.network.resnet import ResNet
+    ref = port.ISTBackbonePort()
+    net = ResNet(dict(n_heads=0, input_dim=3, input_size=256, initial_dim=128, block_dims=[128, 192, 256, 512],
+                      descriptor_size=256))
+    net.load_state_dict(ref.state_dict())
+    net = net.to(DEV).eval()
+    rgb, _ = synth.make_crops(2, seed=31)
+    with torch.no_grad():
+        got = net(rgb.to(DEV)).cpu()
+    g = np.load(os.path.join(golden_dir, "backbones.npz"))
+    want = torch.from_numpy(g["ist_feat_sub"])
+    scale = want.abs().max().item()
+    assert (got[:, ::2] - want).abs().max().item() < 3e-3 * scale
