@@ -189,8 +189,8 @@ int gp_vit_forward(gp_vit_handle_t h, int b, const float* img, float* x_prenorm,
     if (h->attn_mma_sync)
       GPV_CUDA(gp::launch_attention(h->qkv.hi, h->qkv.lo, h->attn.hi, h->attn.lo, b, h->passes, s));
     else
-      GPV_CUDA(gp::launch_attention_tc(h->qkv_hi128, h->qkv_lo128, h->qkv_hi16, h->qkv_lo16, h->attn.hi, h->attn.lo, b,
-                                       h->passes, s));
+      GPV_CUDA(gp::launch_attention_tc(h->qkv_hi128, h->qkv_lo128, h->qkv_hi16, h->qkv_lo16, h->qkv.hi, h->qkv.lo,
+                                       h->attn.hi, h->attn.lo, b, h->passes, s));
     g = gp::GemmParams{}; g.passes = h->passes;
     g.M = M; g.N = kDim; g.K = kDim; g.mode = gp::GEMM_SCALE_RESIDUAL; g.bias = B.proj_b; g.gamma = B.ls1; g.x = h->x;
     GPV_CUDA(gp::launch_vit_gemm(h->attn.m_hi, h->attn.m_lo, B.proj.m_hi, B.proj.m_lo, g, h->num_sms, s));

@@ -8,7 +8,9 @@
 //   O = P V            tcgen05.mma TS, M=128, N=64, K=272          (A = P from TMEM, B = V as MN-major operand)
 //   epilogue           tcgen05.ld O, divide by the row sum, store bf16 hi/lo planes (A operand of the proj GEMM)
 // Both products use the fp32-faithful split: S = Qh Kh + Qh Kl + Ql Kh, O = Ph Vh + Ph Vl + Pl Vh.
-// Warp roles: warp 0 TMA producer (+ TMEM alloc), warp 1 UMMA issuer, warps 2-5 softmax / epilogue.
+// The 257th query row (token 256) would cost a third 128-row tile; one extra warp computes it with fp32 FMAs from the
+// same shared-memory K / V planes while the tensor pipeline runs.
+// Warp roles: warp 0 TMA producer (+ TMEM alloc), warp 1 UMMA issuer, warps 2-5 softmax / epilogue, warp 6 last row.
 #include "gigapose_kernels.h"
 #include "common.cuh"
 #include <cuda_bf16.h>
@@ -22,8 +24,8 @@ constexpr int kKeys = 272;                         // 17 x 16
 constexpr int kRow = 128;                          // bytes per smem row (64 bf16) = SWIZZLE_128B span
 constexpr int kKVPlane = kKeys * kRow;             // 34 KB
 constexpr int kQPlane = 128 * kRow;                // 16 KB
-constexpr int kQTiles = 3;                         // ceil(257 / 128)
-constexpr int kThreads = 6 * 32;
+constexpr int kQTiles = 2;                         // tokens 0..255 on the tensor path; token 256 on one SIMT warp
+constexpr int kThreads = 7 * 32;
 // TMEM columns: S [0,288) (the MMAs write [0,272); P_hi later overwrites [0,144)), P_lo [288,432), O [432,496)
 constexpr uint32_t kColS = 0, kColPlo = 288, kColO = 432;
 constexpr uint32_t kIdescS256 = umma_idesc_f16(128, 256, 1);
@@ -39,12 +41,35 @@ constexpr int kSmem = 1024 + 4 * kKVPlane + 4 * kQPlane + sizeof(AttnTail);
 __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
+// (a, b) -> packed bf16x2 hi word (a in the low half) and the bf16x2 of the residuals: 6 instructions per pair
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// exp(x / 8) = 2^(x * log2(e) / 8); the 1/sqrt(64) logit scale is folded into the constant
+constexpr float kExpScale = 0.125f * 1.4426950408889634f;
+// fp32 value of element `col` of row `row` in a [rows][64] bf16 hi/lo tile stored with the 128-byte TMA swizzle
+// (`lo` may be null: plain bf16 mode)
+__device__ __forceinline__ float2 ld_pair_sw128(const uint8_t* hi, const uint8_t* lo, int row, int col) {
+  const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)col >> 3) ^ ((uint32_t)row & 7u)) << 4) + (((uint32_t)col & 7u) << 1);
+  const uint32_t h = *reinterpret_cast<const uint32_t*>(hi + off);
+  const uint32_t l = lo ? *reinterpret_cast<const uint32_t*>(lo + off) : 0u;
+  return make_float2(__uint_as_float(h << 16) + __uint_as_float(l << 16),
+                     __uint_as_float(h & 0xffff0000u) + __uint_as_float(l & 0xffff0000u));
+}
 
 }  // namespace
 
 __global__ void __launch_bounds__(kThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_constant__ CUtensorMap tm_lo_128,
                     const __grid_constant__ CUtensorMap tm_hi_16, const __grid_constant__ CUtensorMap tm_lo_16,
+                    const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __restrict__ qkv_lo,
                     __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int passes) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -137,7 +162,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
         umma_commit(&tail.o_full);
       }
     }
-  } else {
+  } else if (warp < 6) {
     // ============================== softmax + epilogue (warps 2-5) ==============================
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;                 // query row inside the tile
@@ -147,39 +172,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
       const bool row_ok = tok < kTok;
       mbar_wait(&tail.s_full, qt & 1);
       tc_fence_after();
-      // pass 1: row maximum of the scaled logits over the 257 real keys (9 chunks of 32 columns; columns >= 257 are
-      // padding keys / never-written TMEM and are masked)
+      // pass 1: row maximum of the raw logits over the 257 real keys: 8 full chunks of 32 columns + column 256
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 9; ++c) {
+      for (int c = 0; c < 8; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(tmem + lane_base + kColS + 32 * c, v);
         tmem_ld_wait_for(v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (32 * c + j < kTok) mx = fmaxf(mx, __uint_as_float(v[j]) * 0.125f);
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
       }
-      // pass 2: p = exp(s - max); P goes back to TMEM as packed bf16 pairs (hi over S columns already consumed,
-      // lo next to S); row sum in fp32.  The 1/sqrt(64) scale is an exact power of two.
+      uint32_t tailv[32];                              // columns [256,288): only key 256 is real
+      tmem_ld_32x32(tmem + lane_base + kColS + 256, tailv);
+      tmem_ld_wait_for(tailv);
+      mx = fmaxf(mx, __uint_as_float(tailv[0]));
+      // pass 2: p = exp((s - max) / 8) via ex2; P goes back to TMEM as packed bf16 pairs (hi over S columns already
+      // consumed, lo next to S); row sum in fp32
       float sum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 9; ++c) {
+      for (int c = 0; c < 8; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(tmem + lane_base + kColS + 32 * c, v);
         tmem_ld_wait_for(v);
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int ka = 32 * c + 2 * j, kb = ka + 1;
-          const float pa = ka < kTok ? expf(__uint_as_float(v[2 * j]) * 0.125f - mx) : 0.f;
-          const float pb = kb < kTok ? expf(__uint_as_float(v[2 * j + 1]) * 0.125f - mx) : 0.f;
+          const float pa = ex2_approx((__uint_as_float(v[2 * j]) - mx) * kExpScale);
+          const float pb = ex2_approx((__uint_as_float(v[2 * j + 1]) - mx) * kExpScale);
           sum += pa + pb;
-          const __nv_bfloat16 ah = __float2bfloat16_rn(pa), bh = __float2bfloat16_rn(pb);
-          hi[j] = pack2(ah, bh);
-          lo[j] = pack2(__float2bfloat16_rn(pa - __bfloat162float(ah)), __float2bfloat16_rn(pb - __bfloat162float(bh)));
+          split_pair(pa, pb, hi[j], lo[j]);
         }
         tmem_st_32x16(tmem + lane_base + kColS + 16 * c, hi);       // columns [16c,16c+16) < 32c+32: already read
         tmem_st_32x16(tmem + lane_base + kColPlo + 16 * c, lo);
+      }
+      {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { hi[j] = 0u; lo[j] = 0u; }
+        const float pa = ex2_approx((__uint_as_float(tailv[0]) - mx) * kExpScale);
+        sum += pa;
+        split_pair(pa, 0.f, hi[0], lo[0]);
+        tmem_st_32x16(tmem + lane_base + kColS + 128, hi);          // keys 256..287 (271 used): columns [128,144)
+        tmem_st_32x16(tmem + lane_base + kColPlo + 128, lo);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -198,10 +232,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float a = __uint_as_float(v[2 * j]) * inv, b = __uint_as_float(v[2 * j + 1]) * inv;
-            const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-            hi[j] = pack2(ah, bh);
-            lo[j] = pack2(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
+            split_pair(__uint_as_float(v[2 * j]) * inv, __uint_as_float(v[2 * j + 1]) * inv, hi[j], lo[j]);
           }
           const size_t o = (size_t)(row0 + tok) * kDim + head * kHd + 32 * c;
           uint4* dh = reinterpret_cast<uint4*>(out_hi + o);
@@ -215,6 +246,67 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
       }
       tc_fence_before();                               // O / S reads done before the next tile's MMAs overwrite them
     }
+  } else {
+    // ============================== token 256 on one warp (fp32 FMAs from the smem planes) ==============================
+    __shared__ float s_p[kKeys];
+    mbar_wait(&tail.kv_full, 0);
+    const uint8_t* klo = passes == 3 ? sK[1] : nullptr;   // bf16 mode: the lo planes are not loaded
+    const uint8_t* vlo = passes == 3 ? sV[1] : nullptr;
+    // q (64 values): lane holds q[2*lane], q[2*lane+1]
+    const size_t qoff = (size_t)(row0 + 256) * (3 * kDim) + col_q + 2 * lane;
+    const uint32_t qh = *reinterpret_cast<const uint32_t*>(qkv_hi + qoff);
+    const uint32_t ql = passes == 3 ? *reinterpret_cast<const uint32_t*>(qkv_lo + qoff) : 0u;
+    const float q0 = __uint_as_float(qh << 16) + __uint_as_float(ql << 16);
+    const float q1 = __uint_as_float(qh & 0xffff0000u) + __uint_as_float(ql & 0xffff0000u);
+    // logits: lane handles keys lane, lane+32, ...; the q vector is broadcast with shuffles
+    float sj[9];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const int key = lane + 32 * i;
+      float acc = 0.f;
+      if (key < kTok) {
+#pragma unroll
+        for (int d2 = 0; d2 < 32; ++d2) {
+          const float a0 = __shfl_sync(0xffffffffu, q0, d2), a1 = __shfl_sync(0xffffffffu, q1, d2);
+          const float2 kv = ld_pair_sw128(sK[0], klo, key, 2 * d2);
+          acc = fmaf(a0, kv.x, acc);
+          acc = fmaf(a1, kv.y, acc);
+        }
+      } else {
+#pragma unroll
+        for (int d2 = 0; d2 < 32; ++d2) { (void)__shfl_sync(0xffffffffu, q0, d2); (void)__shfl_sync(0xffffffffu, q1, d2); }
+      }
+      sj[i] = key < kTok ? acc : -INFINITY;
+      mx = fmaxf(mx, sj[i]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const int key = lane + 32 * i;
+      const float pj = key < kTok ? ex2_approx((sj[i] - mx) * kExpScale) : 0.f;
+      sum += pj;
+      if (key < kKeys) s_p[key] = pj;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    __syncwarp();
+    // output: lane handles d = 2*lane, 2*lane+1
+    float o0 = 0.f, o1 = 0.f;
+    for (int key = 0; key < kTok; ++key) {
+      const float2 vv = ld_pair_sw128(sV[0], vlo, key, 2 * lane);
+      const float pj = s_p[key];
+      o0 = fmaf(pj, vv.x, o0);
+      o1 = fmaf(pj, vv.y, o1);
+    }
+    const float inv = 1.0f / sum;
+    uint32_t h, l;
+    split_pair(o0 * inv, o1 * inv, h, l);
+    const size_t oo = (size_t)(row0 + 256) * kDim + head * kHd + 2 * lane;
+    *reinterpret_cast<uint32_t*>(out_hi + oo) = h;
+    *reinterpret_cast<uint32_t*>(out_lo + oo) = l;
   }
 
   tc_fence_before();
@@ -226,8 +318,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
 }
 
 cudaError_t launch_attention_tc(const CUtensorMap& hi128, const CUtensorMap& lo128, const CUtensorMap& hi16,
-                                const CUtensorMap& lo16, uint16_t* out_hi, uint16_t* out_lo, int b, int passes,
-                                cudaStream_t s) {
+                                const CUtensorMap& lo16, const uint16_t* qkv_hi, const uint16_t* qkv_lo, uint16_t* out_hi,
+                                uint16_t* out_lo, int b, int passes, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
@@ -235,7 +327,10 @@ cudaError_t launch_attention_tc(const CUtensorMap& hi128, const CUtensorMap& lo1
     configured = true;
   }
   if (b <= 0) return cudaSuccess;
-  attention_tc_kernel<<<b * kHeads, kThreads, kSmem, s>>>(hi128, lo128, hi16, lo16, reinterpret_cast<__nv_bfloat16*>(out_hi),
+  attention_tc_kernel<<<b * kHeads, kThreads, kSmem, s>>>(hi128, lo128, hi16, lo16,
+                                                         reinterpret_cast<const __nv_bfloat16*>(qkv_hi),
+                                                         reinterpret_cast<const __nv_bfloat16*>(qkv_lo),
+                                                         reinterpret_cast<__nv_bfloat16*>(out_hi),
                                                          reinterpret_cast<__nv_bfloat16*>(out_lo), passes);
   return cudaGetLastError();
 }
