@@ -174,6 +174,7 @@ cudaError_t launch_layernorm_planes(const float* x, int M, const float* w, const
 cudaError_t launch_attention_tc(const CUtensorMap& hi128, const CUtensorMap& lo128, const CUtensorMap& hi16,
                                 const CUtensorMap& lo16, const uint16_t* qkv_hi, const uint16_t* qkv_lo, uint16_t* out_hi,
                                 uint16_t* out_lo, int b, int passes, cudaStream_t s);
+cudaError_t read_attention_stamps(long long* host32);
 cudaError_t launch_attention(const uint16_t* qkv_hi, const uint16_t* qkv_lo, uint16_t* out_hi, uint16_t* out_lo, int b,
                              int passes, cudaStream_t s);
 

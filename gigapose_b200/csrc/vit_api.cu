@@ -163,6 +163,13 @@ int gp_vit_create(int device, int depth, int max_crops, int precision, const flo
   return GP_OK;
 }
 
+int gp_debug_attention_timeline(long long* stamps32) {
+  if (!stamps32) return gp_internal_fail(GP_ERR_INVALID, "null argument");
+  GPV_CUDA(cudaDeviceSynchronize());
+  GPV_CUDA(gp::read_attention_stamps(stamps32));
+  return GP_OK;
+}
+
 int gp_vit_destroy(gp_vit_handle_t h) {
   delete h;
   return GP_OK;

@@ -66,6 +66,10 @@ __device__ __forceinline__ float2 ld_pair_sw128(const uint8_t* hi, const uint8_t
 
 }  // namespace
 
+// cycle stamps of CTA 0 (diagnostics: gp_debug_attention_timeline)
+__device__ long long g_attn_stamp[32];
+#define STAMP(i) do { if (blockIdx.x == 0) g_attn_stamp[i] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(kThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_constant__ CUtensorMap tm_lo_128,
                     const __grid_constant__ CUtensorMap tm_hi_16, const __grid_constant__ CUtensorMap tm_lo_16,
@@ -95,6 +99,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tail.tmem_base;
+  if (threadIdx.x == 0) STAMP(0);
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
@@ -124,6 +129,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
     if (lane == 0) {
       mbar_wait(&tail.kv_full, 0);
       tc_fence_after();
+      STAMP(1);
       const uint32_t kh = smem_u32(sK[0]), kl = smem_u32(sK[1]), vh = smem_u32(sV[0]), vl = smem_u32(sV[1]);
       for (int qt = 0; qt < kQTiles; ++qt) {
         const int buf = qt & 1;
@@ -146,9 +152,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
         }
         umma_commit(&tail.q_empty[buf]);               // Q buffer free once these MMAs retire
         umma_commit(&tail.s_full);
+        STAMP(2 + 4 * qt);
         // O = P V once the softmax warps have written P
         mbar_wait(&tail.p_ready, qt & 1);
         tc_fence_after();
+        STAMP(3 + 4 * qt);
 #pragma unroll 1
         for (int j = 0; j < kKeys / 16; ++j) {         // 17 key steps
           const uint32_t ph = tmem + kColS + 8 * j, pl = tmem + kColPlo + 8 * j;
@@ -160,6 +168,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
           }
         }
         umma_commit(&tail.o_full);
+        STAMP(4 + 4 * qt);
       }
     }
   } else if (warp < 6) {
@@ -172,6 +181,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
       const bool row_ok = tok < kTok;
       mbar_wait(&tail.s_full, qt & 1);
       tc_fence_after();
+      if (warp == 2 && lane == 0) STAMP(12 + 5 * qt);
       // pass 1: row maximum of the raw logits over the 257 real keys: 8 full chunks of 32 columns + column 256
       float mx = -INFINITY;
 #pragma unroll 1
@@ -186,6 +196,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
       tmem_ld_32x32(tmem + lane_base + kColS + 256, tailv);
       tmem_ld_wait_for(tailv);
       mx = fmaxf(mx, __uint_as_float(tailv[0]));
+      if (warp == 2 && lane == 0) STAMP(13 + 5 * qt);
       // pass 2: p = exp((s - max) / 8) via ex2; P goes back to TMEM as packed bf16 pairs (hi over S columns already
       // consumed, lo next to S); row sum in fp32
       float sum = 0.f;
@@ -219,9 +230,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail.p_ready);
+      if (warp == 2 && lane == 0) STAMP(14 + 5 * qt);
       // epilogue: O / sum -> bf16 hi/lo planes
       mbar_wait(&tail.o_full, qt & 1);
       tc_fence_after();
+      if (warp == 2 && lane == 0) STAMP(15 + 5 * qt);
       const float inv = 1.0f / sum;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
@@ -245,11 +258,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
         }
       }
       tc_fence_before();                               // O / S reads done before the next tile's MMAs overwrite them
+      if (warp == 2 && lane == 0) STAMP(16 + 5 * qt);
     }
   } else {
     // ============================== token 256 on one warp (fp32 FMAs from the smem planes) ==============================
     __shared__ float s_p[kKeys];
     mbar_wait(&tail.kv_full, 0);
+    if (lane == 0) STAMP(24);
     const uint8_t* klo = passes == 3 ? sK[1] : nullptr;   // bf16 mode: the lo planes are not loaded
     const uint8_t* vlo = passes == 3 ? sV[1] : nullptr;
     // q (64 values): lane holds q[2*lane], q[2*lane+1]
@@ -293,6 +308,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
     __syncwarp();
+    if (lane == 0) STAMP(25);
     // output: lane handles d = 2*lane, 2*lane+1
     float o0 = 0.f, o1 = 0.f;
     for (int key = 0; key < kTok; ++key) {
@@ -307,6 +323,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
     const size_t oo = (size_t)(row0 + 256) * kDim + head * kHd + 2 * lane;
     *reinterpret_cast<uint32_t*>(out_hi + oo) = h;
     *reinterpret_cast<uint32_t*>(out_lo + oo) = l;
+    if (lane == 0) STAMP(26);
   }
 
   tc_fence_before();
@@ -315,6 +332,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
+}
+
+cudaError_t read_attention_stamps(long long* host32) {
+  return cudaMemcpyFromSymbol(host32, g_attn_stamp, sizeof(long long) * 32);
 }
 
 cudaError_t launch_attention_tc(const CUtensorMap& hi128, const CUtensorMap& lo128, const CUtensorMap& hi16,

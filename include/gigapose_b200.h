@@ -201,6 +201,11 @@ uint64_t gp_launch_count(void);
  * (synchronises the stream); writes the average milliseconds per launch. */
 int gp_time_sim_kernel(gp_handle_t h, int B, int iters, float* avg_ms, void* stream);
 
+/* diagnostics: SM-cycle stamps of CTA 0 of the last attention launch (synchronises the device); 32 int64 values:
+ * [0] start, [1] K/V landed, [2+4t] S issued, [3+4t] P ready, [4+4t] PV issued (t = query tile 0,1),
+ * [12+5t..16+5t] softmax warp: S ready, max done, P written, O ready, O stored; [24..26] last-row warp. */
+int gp_debug_attention_timeline(long long* stamps32);
+
 /* test hook: runs the similarity kernel and additionally dumps the raw fp32 similarity tiles, laid out
  * [item = n * B + j][256 t][256 s] where j indexes the queries sorted by object id (small sizes only). */
 int gp_debug_sim_tiles(gp_handle_t h, int B, float* tiles, void* stream);
