@@ -33,7 +33,7 @@ constexpr uint32_t kIdescS16 = umma_idesc_f16(128, 16, 1);
 constexpr uint32_t kIdescPV = umma_idesc_f16(128, 64, 1, /*B MN-major*/ 1);
 
 struct __align__(8) AttnTail {
-  uint64_t kv_full, q_full[2], q_empty[2], s_full, p_ready, o_full;
+  uint64_t k_full, v_full, q_full[2], q_empty[2], s_full, p_ready, o_full;
   uint32_t tmem_base;
 };
 constexpr int kSmem = 1024 + 4 * kKVPlane + 4 * kQPlane + sizeof(AttnTail);
@@ -87,7 +87,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
   const int col_q = head * kHd, col_k = kDim + head * kHd, col_v = 2 * kDim + head * kHd;
 
   if (threadIdx.x == 0) {
-    mbar_init(&tail.kv_full, 1);
+    mbar_init(&tail.k_full, 1);
+    mbar_init(&tail.v_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&tail.q_full[i], 1); mbar_init(&tail.q_empty[i], 1); }
     mbar_init(&tail.s_full, 1);
     mbar_init(&tail.p_ready, 4);
@@ -105,18 +106,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
     // ============================== TMA producer ==============================
     if (lane == 0) {
       const int np = passes == 3 ? 2 : 1;
-      mbar_arrive_expect_tx(&tail.kv_full, (uint32_t)(2 * np * kKVPlane));
+      tma_prefetch_desc(&tm_hi_128); tma_prefetch_desc(&tm_hi_16);
+      if (np == 2) { tma_prefetch_desc(&tm_lo_128); tma_prefetch_desc(&tm_lo_16); }
+      // order of issue = order of need: Q tile 0, K (for S), then V (only needed after the first softmax)
+      mbar_arrive_expect_tx(&tail.q_full[0], (uint32_t)(np * kQPlane));
+      tma_load_2d(sQ, &tm_hi_128, &tail.q_full[0], col_q, row0);
+      if (np == 2) tma_load_2d(sQ + kQPlane, &tm_lo_128, &tail.q_full[0], col_q, row0);
+      mbar_arrive_expect_tx(&tail.k_full, (uint32_t)(np * kKVPlane));
       for (int pl = 0; pl < np; ++pl) {
         const CUtensorMap* m128 = pl ? &tm_lo_128 : &tm_hi_128;
         const CUtensorMap* m16 = pl ? &tm_lo_16 : &tm_hi_16;
-        tma_load_2d(sK[pl], m128, &tail.kv_full, col_k, row0);
-        tma_load_2d(sK[pl] + 128 * kRow, m128, &tail.kv_full, col_k, row0 + 128);
-        tma_load_2d(sK[pl] + 256 * kRow, m16, &tail.kv_full, col_k, row0 + 256);
-        tma_load_2d(sV[pl], m128, &tail.kv_full, col_v, row0);
-        tma_load_2d(sV[pl] + 128 * kRow, m128, &tail.kv_full, col_v, row0 + 128);
-        tma_load_2d(sV[pl] + 256 * kRow, m16, &tail.kv_full, col_v, row0 + 256);
+        tma_load_2d(sK[pl], m128, &tail.k_full, col_k, row0);
+        tma_load_2d(sK[pl] + 128 * kRow, m128, &tail.k_full, col_k, row0 + 128);
+        tma_load_2d(sK[pl] + 256 * kRow, m16, &tail.k_full, col_k, row0 + 256);
       }
-      for (int qt = 0; qt < kQTiles; ++qt) {
+      mbar_arrive_expect_tx(&tail.v_full, (uint32_t)(np * kKVPlane));
+      for (int pl = 0; pl < np; ++pl) {
+        const CUtensorMap* m128 = pl ? &tm_lo_128 : &tm_hi_128;
+        const CUtensorMap* m16 = pl ? &tm_lo_16 : &tm_hi_16;
+        tma_load_2d(sV[pl], m128, &tail.v_full, col_v, row0);
+        tma_load_2d(sV[pl] + 128 * kRow, m128, &tail.v_full, col_v, row0 + 128);
+        tma_load_2d(sV[pl] + 256 * kRow, m16, &tail.v_full, col_v, row0 + 256);
+      }
+      for (int qt = 1; qt < kQTiles; ++qt) {
         const int buf = qt & 1;
         mbar_wait(&tail.q_empty[buf], ((qt >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&tail.q_full[buf], (uint32_t)(np * kQPlane));
@@ -127,7 +139,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
   } else if (warp == 1) {
     // ============================== UMMA issuer ==============================
     if (lane == 0) {
-      mbar_wait(&tail.kv_full, 0);
+      mbar_wait(&tail.k_full, 0);
       tc_fence_after();
       STAMP(1);
       const uint32_t kh = smem_u32(sK[0]), kl = smem_u32(sK[1]), vh = smem_u32(sV[0]), vl = smem_u32(sV[1]);
@@ -154,10 +166,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
         umma_commit(&tail.s_full);
         STAMP(2 + 4 * qt);
         // O = P V once the softmax warps have written P
+        if (qt == 0) mbar_wait(&tail.v_full, 0);
         mbar_wait(&tail.p_ready, qt & 1);
         tc_fence_after();
         STAMP(3 + 4 * qt);
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < kKeys / 16; ++j) {         // 17 key steps
           const uint32_t ph = tmem + kColS + 8 * j, pl = tmem + kColPlo + 8 * j;
           const uint64_t dvh = umma_desc_mnmajor_sw128(vh + j * 16 * kRow), dvl = umma_desc_mnmajor_sw128(vl + j * 16 * kRow);
@@ -199,23 +212,35 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
       if (warp == 2 && lane == 0) STAMP(13 + 5 * qt);
       // pass 2: p = exp((s - max) / 8) via ex2; P goes back to TMEM as packed bf16 pairs (hi over S columns already
       // consumed, lo next to S); row sum in fp32
-      float sum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem + lane_base + kColS + 32 * c, v);
-        tmem_ld_wait_for(v);
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      auto do_chunk = [&](uint32_t (&v)[32], int c) {
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float pa = ex2_approx((__uint_as_float(v[2 * j]) - mx) * kExpScale);
           const float pb = ex2_approx((__uint_as_float(v[2 * j + 1]) - mx) * kExpScale);
-          sum += pa + pb;
+          sum4[j & 3] += pa + pb;
           split_pair(pa, pb, hi[j], lo[j]);
         }
         tmem_st_32x16(tmem + lane_base + kColS + 16 * c, hi);       // columns [16c,16c+16) < 32c+32: already read
         tmem_st_32x16(tmem + lane_base + kColPlo + 16 * c, lo);
+      };
+      {   // software-pipelined: chunk c+1 is in flight while chunk c is processed (it is read before the P store of
+          // chunk c can touch it: P columns of chunk c end at 16c+16 <= 32(c+1))
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(tmem + lane_base + kColS, va);
+        tmem_ld_wait_for(va);
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+          tmem_ld_32x32(tmem + lane_base + kColS + 32 * (c + 1), vb);      // in flight during chunk c
+          do_chunk(va, c);
+          tmem_ld_wait_for(vb);
+          if (c + 2 < 8) tmem_ld_32x32(tmem + lane_base + kColS + 32 * (c + 2), va);   // in flight during chunk c+1
+          do_chunk(vb, c + 1);
+          if (c + 2 < 8) tmem_ld_wait_for(va);
+        }
       }
+      float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       {
         uint32_t hi[16], lo[16];
 #pragma unroll
@@ -263,17 +288,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
   } else {
     // ============================== token 256 on one warp (fp32 FMAs from the smem planes) ==============================
     __shared__ float s_p[kKeys];
-    mbar_wait(&tail.kv_full, 0);
-    if (lane == 0) STAMP(24);
-    const uint8_t* klo = passes == 3 ? sK[1] : nullptr;   // bf16 mode: the lo planes are not loaded
-    const uint8_t* vlo = passes == 3 ? sV[1] : nullptr;
-    // q (64 values): lane holds q[2*lane], q[2*lane+1]
+    __shared__ float s_q[kHd];
+    // q (64 values): lane loads q[2*lane], q[2*lane+1] straight from the planes and shares them through smem
     const size_t qoff = (size_t)(row0 + 256) * (3 * kDim) + col_q + 2 * lane;
     const uint32_t qh = *reinterpret_cast<const uint32_t*>(qkv_hi + qoff);
     const uint32_t ql = passes == 3 ? *reinterpret_cast<const uint32_t*>(qkv_lo + qoff) : 0u;
-    const float q0 = __uint_as_float(qh << 16) + __uint_as_float(ql << 16);
-    const float q1 = __uint_as_float(qh & 0xffff0000u) + __uint_as_float(ql & 0xffff0000u);
-    // logits: lane handles keys lane, lane+32, ...; the q vector is broadcast with shuffles
+    s_q[2 * lane] = __uint_as_float(qh << 16) + __uint_as_float(ql << 16);
+    s_q[2 * lane + 1] = __uint_as_float(qh & 0xffff0000u) + __uint_as_float(ql & 0xffff0000u);
+    __syncwarp();
+    mbar_wait(&tail.k_full, 0);
+    if (lane == 0) STAMP(24);
+    const uint8_t* klo = passes == 3 ? sK[1] : nullptr;   // bf16 mode: the lo planes are not loaded
+    const uint8_t* vlo = passes == 3 ? sV[1] : nullptr;
+    // logits: lane handles keys lane, lane+32, ...; one 16-byte chunk (8 channels) of a K row per load
     float sj[9];
     float mx = -INFINITY;
 #pragma unroll
@@ -282,15 +309,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
       float acc = 0.f;
       if (key < kTok) {
 #pragma unroll
-        for (int d2 = 0; d2 < 32; ++d2) {
-          const float a0 = __shfl_sync(0xffffffffu, q0, d2), a1 = __shfl_sync(0xffffffffu, q1, d2);
-          const float2 kv = ld_pair_sw128(sK[0], klo, key, 2 * d2);
-          acc = fmaf(a0, kv.x, acc);
-          acc = fmaf(a1, kv.y, acc);
-        }
-      } else {
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint32_t off = (uint32_t)key * 128u + (((uint32_t)ch ^ ((uint32_t)key & 7u)) << 4);
+          const uint4 h4 = *reinterpret_cast<const uint4*>(sK[0] + off);
+          const uint4 l4 = klo ? *reinterpret_cast<const uint4*>(klo + off) : make_uint4(0, 0, 0, 0);
+          const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
-        for (int d2 = 0; d2 < 32; ++d2) { (void)__shfl_sync(0xffffffffu, q0, d2); (void)__shfl_sync(0xffffffffu, q1, d2); }
+          for (int w = 0; w < 4; ++w) {
+            const float k0 = __uint_as_float(hw[w] << 16) + __uint_as_float(lw[w] << 16);
+            const float k1 = __uint_as_float(hw[w] & 0xffff0000u) + __uint_as_float(lw[w] & 0xffff0000u);
+            acc = fmaf(s_q[ch * 8 + 2 * w], k0, acc);
+            acc = fmaf(s_q[ch * 8 + 2 * w + 1], k1, acc);
+          }
+        }
       }
       sj[i] = key < kTok ? acc : -INFINITY;
       mx = fmaxf(mx, sj[i]);
@@ -309,17 +340,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
     for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
     __syncwarp();
     if (lane == 0) STAMP(25);
-    // output: lane handles d = 2*lane, 2*lane+1
-    float o0 = 0.f, o1 = 0.f;
-    for (int key = 0; key < kTok; ++key) {
+    mbar_wait(&tail.v_full, 0);
+    // output: lane handles d = 2*lane, 2*lane+1 (4 partial accumulators, loads batched by the unroll)
+    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int key = 0; key < 256; ++key) {
       const float2 vv = ld_pair_sw128(sV[0], vlo, key, 2 * lane);
       const float pj = s_p[key];
-      o0 = fmaf(pj, vv.x, o0);
-      o1 = fmaf(pj, vv.y, o1);
+      o0[key & 3] = fmaf(pj, vv.x, o0[key & 3]);
+      o1[key & 3] = fmaf(pj, vv.y, o1[key & 3]);
     }
+    {
+      const float2 vv = ld_pair_sw128(sV[0], vlo, 256, 2 * lane);
+      o0[0] = fmaf(s_p[256], vv.x, o0[0]);
+      o1[0] = fmaf(s_p[256], vv.y, o1[0]);
+    }
+    const float o0s = (o0[0] + o0[1]) + (o0[2] + o0[3]), o1s = (o1[0] + o1[1]) + (o1[2] + o1[3]);
     const float inv = 1.0f / sum;
     uint32_t h, l;
-    split_pair(o0 * inv, o1 * inv, h, l);
+    split_pair(o0s * inv, o1s * inv, h, l);
     const size_t oo = (size_t)(row0 + 256) * kDim + head * kHd + 2 * lane;
     *reinterpret_cast<uint32_t*>(out_hi + oo) = h;
     *reinterpret_cast<uint32_t*>(out_lo + oo) = l;
