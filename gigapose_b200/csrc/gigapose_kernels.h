@@ -152,7 +152,7 @@ cudaError_t launch_pose_only(int n, int k, int T, const int* q_obj, const float*
                              const float* tmpl_pose, float* poses, cudaStream_t stream);
 
 // ---------------------------------------------------------------- ViT-L/14 (vit_gemm.cu, vit_ops.cu)
-enum GemmMode { GEMM_PLANES = 0, GEMM_PLANES_GELU = 1, GEMM_SCALE_RESIDUAL = 2, GEMM_PATCH_EMBED = 3 };
+enum GemmMode { GEMM_PLANES = 0, GEMM_PLANES_GELU = 1, GEMM_SCALE_RESIDUAL = 2, GEMM_PATCH_EMBED = 3, GEMM_QKV_HEADS = 4 };
 struct GemmParams {
   int M, N, K;                // C[M,N] = A[M,K] W[N,K]^T ; N % 256 == 0, K % 32 == 0
   int passes;                 // 3 = hi*hi + hi*lo + lo*hi, 1 = hi*hi
@@ -163,6 +163,7 @@ struct GemmParams {
   uint16_t *out_hi, *out_lo;  // bf16 planes [M,N] (GEMM_PLANES*)
   const float* pos;           // [257,N] positional table (GEMM_PATCH_EMBED)
   int tokens_per_img, patches_per_img;
+  int qkv_crop_stride;        // GEMM_QKV_HEADS: crops per q/k/v section of the head-major planes (= max_crops)
 };
 cudaError_t launch_vit_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                             const CUtensorMap& w_lo, const GemmParams& p, int num_sms, cudaStream_t stream);
@@ -173,9 +174,7 @@ cudaError_t launch_layernorm_planes(const float* x, int M, const float* w, const
                                     uint16_t* lo, cudaStream_t s);
 cudaError_t launch_attention_tc(const CUtensorMap& hi128, const CUtensorMap& lo128, const CUtensorMap& hi16,
                                 const CUtensorMap& lo16, const uint16_t* qkv_hi, const uint16_t* qkv_lo, uint16_t* out_hi,
-                                uint16_t* out_lo, int b, int passes, cudaStream_t s);
+                                uint16_t* out_lo, int b, int crop_stride, int passes, cudaStream_t s);
 cudaError_t read_attention_stamps(long long* host32);
-cudaError_t launch_attention(const uint16_t* qkv_hi, const uint16_t* qkv_lo, uint16_t* out_hi, uint16_t* out_lo, int b,
-                             int passes, cudaStream_t s);
 
 }  // namespace gp

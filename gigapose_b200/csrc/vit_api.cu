@@ -54,7 +54,6 @@ struct gp_vit_context {
   float* x;                    // [max_crops*257, 1024] residual stream
   Planes ln, qkv, attn, hid, patches;   // activation planes (+ TMA maps for those that feed a GEMM)
   CUtensorMap qkv_hi128, qkv_lo128, qkv_hi16, qkv_lo16;   // attention operand tiles: 64 columns x {128,16} token rows
-  bool attn_mma_sync;                   // GIGAPOSE_ATTN=mma selects the warp-level MMA kernel (A/B testing)
   size_t workspace_bytes;
 };
 
@@ -129,8 +128,7 @@ int gp_vit_create(int device, int depth, int max_crops, int precision, const flo
   // activation planes start finite: the attention tiles read up to 15 token rows past a crop (masked keys, P = 0),
   // and 0 * NaN from never-written memory would poison the P.V accumulation
   if (cudaMemsetAsync(workspace_mem, 0, cs.off, s) != cudaSuccess) { delete h; return gp_internal_fail(GP_ERR_CUDA, "workspace memset failed"); }
-  const char* attn_env = getenv("GIGAPOSE_ATTN");
-  h->attn_mma_sync = attn_env && std::string(attn_env) == "mma";
+
   // pack weights: fp32 [N,K] -> bf16 hi/lo planes (patch embedding padded 588 -> 608 columns)
   h->patch_b = w[1]; h->cls = w[2]; h->pos = w[3];
   cudaError_t ce = gp::launch_split_planes(w[0], kDim, kPatchK, kPatchKPad, h->patch_w.hi, h->patch_w.lo, s);
@@ -152,10 +150,10 @@ int gp_vit_create(int device, int depth, int max_crops, int precision, const flo
   if (!e && ce == cudaSuccess)
     (e = make_maps(&h->ln, M, kDim, 128)) || (e = make_maps(&h->attn, M, kDim, 128)) || (e = make_maps(&h->hid, M, kMlp, 128)) ||
         (e = make_maps(&h->patches, (uint64_t)max_crops * 256, kPatchKPad, 128)) ||
-        (e = gp_internal_make_map_ex(&h->qkv_hi128, h->qkv.hi, M, kQkv, 64, 128, 128)) ||
-        (e = gp_internal_make_map_ex(&h->qkv_lo128, h->qkv.lo, M, kQkv, 64, 128, 128)) ||
-        (e = gp_internal_make_map_ex(&h->qkv_hi16, h->qkv.hi, M, kQkv, 64, 16, 128)) ||
-        (e = gp_internal_make_map_ex(&h->qkv_lo16, h->qkv.lo, M, kQkv, 64, 16, 128));
+        (e = gp_internal_make_map_ex(&h->qkv_hi128, h->qkv.hi, 48 * M, 64, 64, 128, 128)) ||   // rows = 3*crops*16*257
+        (e = gp_internal_make_map_ex(&h->qkv_lo128, h->qkv.lo, 48 * M, 64, 64, 128, 128)) ||
+        (e = gp_internal_make_map_ex(&h->qkv_hi16, h->qkv.hi, 48 * M, 64, 64, 16, 128)) ||
+        (e = gp_internal_make_map_ex(&h->qkv_lo16, h->qkv.lo, 48 * M, 64, 64, 16, 128));
   if (ce != cudaSuccess) { delete h; return gp_internal_fail(GP_ERR_CUDA, "weight packing failed: %s", cudaGetErrorString(ce)); }
   if (e) { delete h; return e; }
   gp_internal_count_launches(1 + 4 * depth);
@@ -191,13 +189,11 @@ int gp_vit_forward(gp_vit_handle_t h, int b, const float* img, float* x_prenorm,
     const BlockW& B = h->blocks[i];
     GPV_CUDA(gp::launch_layernorm_planes(h->x, M, B.n1w, B.n1b, 1e-6f, h->ln.hi, h->ln.lo, s));
     g = gp::GemmParams{}; g.passes = h->passes;
-    g.M = M; g.N = kQkv; g.K = kDim; g.mode = gp::GEMM_PLANES; g.bias = B.qkv_b; g.out_hi = h->qkv.hi; g.out_lo = h->qkv.lo;
+    g.M = M; g.N = kQkv; g.K = kDim; g.mode = gp::GEMM_QKV_HEADS; g.bias = B.qkv_b; g.out_hi = h->qkv.hi; g.out_lo = h->qkv.lo;
+    g.tokens_per_img = kTok; g.qkv_crop_stride = h->max_crops;
     GPV_CUDA(gp::launch_vit_gemm(h->ln.m_hi, h->ln.m_lo, B.qkv.m_hi, B.qkv.m_lo, g, h->num_sms, s));
-    if (h->attn_mma_sync)
-      GPV_CUDA(gp::launch_attention(h->qkv.hi, h->qkv.lo, h->attn.hi, h->attn.lo, b, h->passes, s));
-    else
-      GPV_CUDA(gp::launch_attention_tc(h->qkv_hi128, h->qkv_lo128, h->qkv_hi16, h->qkv_lo16, h->qkv.hi, h->qkv.lo,
-                                       h->attn.hi, h->attn.lo, b, h->passes, s));
+    GPV_CUDA(gp::launch_attention_tc(h->qkv_hi128, h->qkv_lo128, h->qkv_hi16, h->qkv_lo16, h->qkv.hi, h->qkv.lo,
+                                     h->attn.hi, h->attn.lo, b, h->max_crops, h->passes, s));
     g = gp::GemmParams{}; g.passes = h->passes;
     g.M = M; g.N = kDim; g.K = kDim; g.mode = gp::GEMM_SCALE_RESIDUAL; g.bias = B.proj_b; g.gamma = B.ls1; g.x = h->x;
     GPV_CUDA(gp::launch_vit_gemm(h->attn.m_hi, h->attn.m_lo, B.proj.m_hi, B.proj.m_lo, g, h->num_sms, s));

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_constant__ CUtensorMap tm_lo_128,
                     const __grid_constant__ CUtensorMap tm_hi_16, const __grid_constant__ CUtensorMap tm_lo_16,
                     const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __restrict__ qkv_lo,
-                    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int passes) {
+                    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int crop_stride, int passes) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sK[2] = {smem, smem + kKVPlane};                                   // hi, lo
@@ -83,8 +83,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
   AttnTail& tail = *reinterpret_cast<AttnTail*>(smem + 4 * kKVPlane + 4 * kQPlane);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int img = blockIdx.x / kHeads, head = blockIdx.x % kHeads;
-  const int row0 = img * kTok;                       // first token row of this crop in the [M, 3072] planes
-  const int col_q = head * kHd, col_k = kDim + head * kHd, col_v = 2 * kDim + head * kHd;
+  const int row0 = img * kTok;                       // first token row of this crop in the [M, 1024] output planes
+  // head-major operand planes [q|k|v][crop][head][token][64]: first row of this (crop, head) in each section
+  const int rq = ((0 * crop_stride + img) * kHeads + head) * kTok;
+  const int rk = ((1 * crop_stride + img) * kHeads + head) * kTok;
+  const int rv = ((2 * crop_stride + img) * kHeads + head) * kTok;
 
   if (threadIdx.x == 0) {
     mbar_init(&tail.k_full, 1);
@@ -110,30 +113,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
       if (np == 2) { tma_prefetch_desc(&tm_lo_128); tma_prefetch_desc(&tm_lo_16); }
       // order of issue = order of need: Q tile 0, K (for S), then V (only needed after the first softmax)
       mbar_arrive_expect_tx(&tail.q_full[0], (uint32_t)(np * kQPlane));
-      tma_load_2d(sQ, &tm_hi_128, &tail.q_full[0], col_q, row0);
-      if (np == 2) tma_load_2d(sQ + kQPlane, &tm_lo_128, &tail.q_full[0], col_q, row0);
+      tma_load_2d(sQ, &tm_hi_128, &tail.q_full[0], 0, rq);
+      if (np == 2) tma_load_2d(sQ + kQPlane, &tm_lo_128, &tail.q_full[0], 0, rq);
       mbar_arrive_expect_tx(&tail.k_full, (uint32_t)(np * kKVPlane));
       for (int pl = 0; pl < np; ++pl) {
         const CUtensorMap* m128 = pl ? &tm_lo_128 : &tm_hi_128;
         const CUtensorMap* m16 = pl ? &tm_lo_16 : &tm_hi_16;
-        tma_load_2d(sK[pl], m128, &tail.k_full, col_k, row0);
-        tma_load_2d(sK[pl] + 128 * kRow, m128, &tail.k_full, col_k, row0 + 128);
-        tma_load_2d(sK[pl] + 256 * kRow, m16, &tail.k_full, col_k, row0 + 256);
+        tma_load_2d(sK[pl], m128, &tail.k_full, 0, rk);
+        tma_load_2d(sK[pl] + 128 * kRow, m128, &tail.k_full, 0, rk + 128);
+        tma_load_2d(sK[pl] + 256 * kRow, m16, &tail.k_full, 0, rk + 256);
       }
       mbar_arrive_expect_tx(&tail.v_full, (uint32_t)(np * kKVPlane));
       for (int pl = 0; pl < np; ++pl) {
         const CUtensorMap* m128 = pl ? &tm_lo_128 : &tm_hi_128;
         const CUtensorMap* m16 = pl ? &tm_lo_16 : &tm_hi_16;
-        tma_load_2d(sV[pl], m128, &tail.v_full, col_v, row0);
-        tma_load_2d(sV[pl] + 128 * kRow, m128, &tail.v_full, col_v, row0 + 128);
-        tma_load_2d(sV[pl] + 256 * kRow, m16, &tail.v_full, col_v, row0 + 256);
+        tma_load_2d(sV[pl], m128, &tail.v_full, 0, rv);
+        tma_load_2d(sV[pl] + 128 * kRow, m128, &tail.v_full, 0, rv + 128);
+        tma_load_2d(sV[pl] + 256 * kRow, m16, &tail.v_full, 0, rv + 256);
       }
       for (int qt = 1; qt < kQTiles; ++qt) {
         const int buf = qt & 1;
         mbar_wait(&tail.q_empty[buf], ((qt >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&tail.q_full[buf], (uint32_t)(np * kQPlane));
-        tma_load_2d(sQ + (buf * 2 + 0) * kQPlane, &tm_hi_128, &tail.q_full[buf], col_q, row0 + qt * 128);
-        if (np == 2) tma_load_2d(sQ + (buf * 2 + 1) * kQPlane, &tm_lo_128, &tail.q_full[buf], col_q, row0 + qt * 128);
+        tma_load_2d(sQ + (buf * 2 + 0) * kQPlane, &tm_hi_128, &tail.q_full[buf], 0, rq + qt * 128);
+        if (np == 2) tma_load_2d(sQ + (buf * 2 + 1) * kQPlane, &tm_lo_128, &tail.q_full[buf], 0, rq + qt * 128);
       }
     }
   } else if (warp == 1) {
@@ -290,7 +293,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
     __shared__ float s_p[kKeys];
     __shared__ float s_q[kHd];
     // q (64 values): lane loads q[2*lane], q[2*lane+1] straight from the planes and shares them through smem
-    const size_t qoff = (size_t)(row0 + 256) * (3 * kDim) + col_q + 2 * lane;
+    const size_t qoff = (size_t)(rq + 256) * kHd + 2 * lane;
     const uint32_t qh = *reinterpret_cast<const uint32_t*>(qkv_hi + qoff);
     const uint32_t ql = passes == 3 ? *reinterpret_cast<const uint32_t*>(qkv_lo + qoff) : 0u;
     s_q[2 * lane] = __uint_as_float(qh << 16) + __uint_as_float(ql << 16);
@@ -379,7 +382,7 @@ cudaError_t read_attention_stamps(long long* host32) {
 
 cudaError_t launch_attention_tc(const CUtensorMap& hi128, const CUtensorMap& lo128, const CUtensorMap& hi16,
                                 const CUtensorMap& lo16, const uint16_t* qkv_hi, const uint16_t* qkv_lo, uint16_t* out_hi,
-                                uint16_t* out_lo, int b, int passes, cudaStream_t s) {
+                                uint16_t* out_lo, int b, int crop_stride, int passes, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
@@ -391,7 +394,7 @@ cudaError_t launch_attention_tc(const CUtensorMap& hi128, const CUtensorMap& lo1
                                                          reinterpret_cast<const __nv_bfloat16*>(qkv_hi),
                                                          reinterpret_cast<const __nv_bfloat16*>(qkv_lo),
                                                          reinterpret_cast<__nv_bfloat16*>(out_hi),
-                                                         reinterpret_cast<__nv_bfloat16*>(out_lo), passes);
+                                                         reinterpret_cast<__nv_bfloat16*>(out_lo), crop_stride, passes);
   return cudaGetLastError();
 }
 

@@ -175,7 +175,7 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(v32[j]) + sb[c0 + j];
-        if (p.mode == GEMM_PLANES || p.mode == GEMM_PLANES_GELU) {
+        if (p.mode == GEMM_PLANES || p.mode == GEMM_PLANES_GELU || p.mode == GEMM_QKV_HEADS) {
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
@@ -185,8 +185,14 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             hi[j >> 1] = pack_bf16(ah, bh);
             lo[j >> 1] = pack_bf16(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
           }
-          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + out_row * p.N + n);
-          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + out_row * p.N + n);
+          size_t dst = out_row * p.N + n;
+          if (p.mode == GEMM_QKV_HEADS) {   // head-major: [q|k|v][crop][head][token][64] so that attention tiles are contiguous
+            const int which = n >> 10, head = (n & 1023) >> 6, d0 = n & 63;
+            const int img = m / p.tokens_per_img, tok = m - img * p.tokens_per_img;
+            dst = ((((size_t)which * p.qkv_crop_stride + img) * 16 + head) * p.tokens_per_img + tok) * 64 + d0;
+          }
+          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + dst);
+          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + dst);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
