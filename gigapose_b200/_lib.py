@@ -78,6 +78,7 @@ SYMBOLS = {
     "gp_vit_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gp_launch_count": (C.c_uint64, []),
     "gp_debug_attention_timeline": (C.c_int, [C.c_void_p]),
+    "gp_debug_gemm_timeline": (C.c_int, [C.c_void_p]),
     "gp_debug_sim_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "gp_time_sim_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
 }

@@ -176,5 +176,6 @@ cudaError_t launch_attention_tc(const CUtensorMap& hi128, const CUtensorMap& lo1
                                 const CUtensorMap& lo16, const uint16_t* qkv_hi, const uint16_t* qkv_lo, uint16_t* out_hi,
                                 uint16_t* out_lo, int b, int crop_stride, int passes, cudaStream_t s);
 cudaError_t read_attention_stamps(long long* host32);
+cudaError_t read_gemm_stamps(long long* host64);
 
 }  // namespace gp

@@ -168,6 +168,13 @@ int gp_debug_attention_timeline(long long* stamps32) {
   return GP_OK;
 }
 
+int gp_debug_gemm_timeline(long long* stamps64) {
+  if (!stamps64) return gp_internal_fail(GP_ERR_INVALID, "null argument");
+  GPV_CUDA(cudaDeviceSynchronize());
+  GPV_CUDA(gp::read_gemm_stamps(stamps64));
+  return GP_OK;
+}
+
 int gp_vit_destroy(gp_vit_handle_t h) {
   delete h;
   return GP_OK;

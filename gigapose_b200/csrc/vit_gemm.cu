@@ -60,6 +60,11 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
 
 }  // namespace
 
+// cycle stamps of CTA 0 for the QKV-shaped GEMM (diagnostics: gp_debug_gemm_timeline): [tile][0..3] =
+// UMMA start, UMMA issued, epilogue start, epilogue end; [63] = kernel start
+__device__ long long g_gemm_stamp[64];
+#define GSTAMP(i) do { if (blockIdx.x == 0 && p.N == 3072 && (i) < 64) g_gemm_stamp[i] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(kThreads, 1)
 vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, GemmParams p) {
@@ -86,6 +91,7 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tail.tmem_base;
+  if (threadIdx.x == 0) GSTAMP(63);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -116,6 +122,7 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         const uint32_t acc = unit & 1u;
         mbar_wait(&tail.tmem_empty_bar[acc], ((unit >> 1) & 1u) ^ 1u);
         tc_fence_after();
+        GSTAMP(unit * 4 + 0);
         const uint32_t d = tmem_base + acc * 256;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&tail.full_bar[stage], phase);
@@ -136,6 +143,7 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tail.tmem_full_bar[acc]);
+        GSTAMP(unit * 4 + 1);
       }
     }
   } else if (warp >= 4) {
@@ -168,6 +176,7 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       // residual rows are prefetched before the accumulator is ready (GEMM_SCALE_RESIDUAL reads what it overwrites)
       mbar_wait(&tail.tmem_full_bar[acc], (unit >> 1) & 1u);
       tc_fence_after();
+      if (e == 0 && lane == 0) GSTAMP(unit * 4 + 2);
 
       auto process = [&](uint32_t (&v32)[32], int c0) {
         if (!row_ok) return;
@@ -245,6 +254,7 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail.tmem_empty_bar[acc]);
       process(vb, 96);
+      if (e == 0 && lane == 0) GSTAMP(unit * 4 + 3);
     }
   }
 
@@ -255,6 +265,8 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     tmem_dealloc(tmem_base, 512);
   }
 }
+
+cudaError_t read_gemm_stamps(long long* host64) { return cudaMemcpyFromSymbol(host64, g_gemm_stamp, sizeof(long long) * 64); }
 
 cudaError_t launch_vit_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                             const CUtensorMap& w_lo, const GemmParams& p, int num_sms, cudaStream_t stream) {

@@ -205,6 +205,9 @@ int gp_time_sim_kernel(gp_handle_t h, int B, int iters, float* avg_ms, void* str
  * [0] start, [1] K/V landed, [2+4t] S issued, [3+4t] P ready, [4+4t] PV issued (t = query tile 0,1),
  * [12+5t..16+5t] softmax warp: S ready, max done, P written, O ready, O stored; [24..26] last-row warp. */
 int gp_debug_attention_timeline(long long* stamps32);
+/* same for CTA 0 of the last QKV-shaped ViT GEMM: 64 int64: [4*tile + {0: UMMA start, 1: UMMA issued, 2: epilogue
+ * start, 3: epilogue end}], [63] = kernel start. */
+int gp_debug_gemm_timeline(long long* stamps64);
 
 /* test hook: runs the similarity kernel and additionally dumps the raw fp32 similarity tiles, laid out
  * [item = n * B + j][256 t][256 s] where j indexes the queries sorted by object id (small sizes only). */
