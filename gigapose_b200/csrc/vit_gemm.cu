@@ -31,6 +31,7 @@ constexpr uint32_t kIdesc = umma_idesc_f16(kBM, kBN, 1);
 struct __align__(8) GemmSmemTail {
   float bias_s[2][kBN];                           // per-tile bias / LayerScale columns, double buffered with the accumulator
   float gamma_s[2][kBN];
+  uint8_t stage_buf[kEpiWarps][32 * 80];          // per-warp transposition buffer: 32 rows x (64 B + 16 B pad)
   uint64_t full_bar[kStages];
   uint64_t empty_bar[kStages];
   uint64_t tmem_full_bar[2];
@@ -178,8 +179,45 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       tc_fence_after();
       if (e == 0 && lane == 0) GSTAMP(unit * 4 + 2);
 
+      uint8_t* stg = tail.stage_buf[e];
+      const unsigned okmask = __ballot_sync(0xffffffffu, row_ok);
+      // One warp-wide store instruction of the natural "thread = row" mapping touches 32 different rows with 16 bytes
+      // each (32 half-written sectors).  Rows are therefore transposed through a small smem buffer so that 4 (bf16
+      // planes) or 4 (fp32, in two 16-column halves) consecutive lanes cover one contiguous 64-byte row segment:
+      // every global transaction is a fully written 32-byte sector and an instruction touches 8 rows instead of 32.
+      auto store_rows_64B = [&](const uint32_t (&w)[16], uint8_t* base, size_t row_byte_off) {
+        uint4* srow = reinterpret_cast<uint4*>(stg + lane * 80);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) srow[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        __syncwarp();
+        const uint32_t off_lo = (uint32_t)row_byte_off, off_hi = (uint32_t)(row_byte_off >> 32);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + (lane >> 2), piece = lane & 3;
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 80 + piece * 16);
+          const size_t o = ((size_t)__shfl_sync(0xffffffffu, off_hi, rr) << 32) | __shfl_sync(0xffffffffu, off_lo, rr);
+          if ((okmask >> rr) & 1u) *reinterpret_cast<uint4*>(base + o + piece * 16) = val;
+        }
+        __syncwarp();
+      };
+      auto load_rows_64B = [&](uint32_t (&w)[16], const uint8_t* base, size_t row_byte_off) {
+        const uint32_t off_lo = (uint32_t)row_byte_off, off_hi = (uint32_t)(row_byte_off >> 32);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + (lane >> 2), piece = lane & 3;
+          const size_t o = ((size_t)__shfl_sync(0xffffffffu, off_hi, rr) << 32) | __shfl_sync(0xffffffffu, off_lo, rr);
+          uint4 val = make_uint4(0, 0, 0, 0);
+          if ((okmask >> rr) & 1u) val = *reinterpret_cast<const uint4*>(base + o + piece * 16);
+          *reinterpret_cast<uint4*>(stg + rr * 80 + piece * 16) = val;
+        }
+        __syncwarp();
+        const uint4* srow = reinterpret_cast<const uint4*>(stg + lane * 80);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const uint4 t = srow[j]; w[4 * j] = t.x; w[4 * j + 1] = t.y; w[4 * j + 2] = t.z; w[4 * j + 3] = t.w; }
+        __syncwarp();
+      };
+
       auto process = [&](uint32_t (&v32)[32], int c0) {
-        if (!row_ok) return;
         const int n = n0 + c0;
         float v[32];
 #pragma unroll
@@ -200,38 +238,28 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             const int img = m / p.tokens_per_img, tok = m - img * p.tokens_per_img;
             dst = ((((size_t)which * p.qkv_crop_stride + img) * 16 + head) * p.tokens_per_img + tok) * 64 + d0;
           }
-          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + dst);
-          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + dst);
+          store_rows_64B(hi, reinterpret_cast<uint8_t*>(p.out_hi), dst * 2);
+          store_rows_64B(lo, reinterpret_cast<uint8_t*>(p.out_lo), dst * 2);
+        } else if (p.mode == GEMM_SCALE_RESIDUAL) {      // x += gamma * (acc + bias)   (blocks: ls1 / ls2 + residual)
+          const size_t rowb = (out_row * p.N + n) * 4;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-            dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          for (int half = 0; half < 2; ++half) {
+            uint32_t w[16];
+            load_rows_64B(w, reinterpret_cast<const uint8_t*>(p.x), rowb + half * 64);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              w[j] = __float_as_uint(__uint_as_float(w[j]) + sg[c0 + half * 16 + j] * v[half * 16 + j]);
+            store_rows_64B(w, reinterpret_cast<uint8_t*>(p.x), rowb + half * 64);
           }
-        } else {
-          float4* dst = reinterpret_cast<float4*>(p.x + out_row * p.N + n);
-          if (p.mode == GEMM_SCALE_RESIDUAL) {         // x += gamma * (acc + bias)   (blocks: ls1 / ls2 + residual)
-            float4 xr[8];
+        } else {                                          // GEMM_PATCH_EMBED
+          const size_t rowb = (out_row * p.N + n) * 4;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) xr[j] = dst[j];
+          for (int half = 0; half < 2; ++half) {
+            uint32_t w[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 o;
-              o.x = xr[j].x + sg[c0 + 4 * j + 0] * v[4 * j + 0];
-              o.y = xr[j].y + sg[c0 + 4 * j + 1] * v[4 * j + 1];
-              o.z = xr[j].z + sg[c0 + 4 * j + 2] * v[4 * j + 2];
-              o.w = xr[j].w + sg[c0 + 4 * j + 3] * v[4 * j + 3];
-              dst[j] = o;
-            }
-          } else {                                      // GEMM_PATCH_EMBED
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 o;
-              o.x = v[4 * j + 0] + __ldg(pos_row + n + 4 * j + 0);
-              o.y = v[4 * j + 1] + __ldg(pos_row + n + 4 * j + 1);
-              o.z = v[4 * j + 2] + __ldg(pos_row + n + 4 * j + 2);
-              o.w = v[4 * j + 3] + __ldg(pos_row + n + 4 * j + 3);
-              dst[j] = o;
-            }
+            for (int j = 0; j < 16; ++j)
+              w[j] = __float_as_uint(v[half * 16 + j] + (row_ok ? __ldg(pos_row + n + half * 16 + j) : 0.f));
+            store_rows_64B(w, reinterpret_cast<uint8_t*>(p.x), rowb + half * 64);
           }
         }
       };
