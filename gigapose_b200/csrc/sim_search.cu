@@ -42,6 +42,20 @@ constexpr int kThreads = 4 * 32 + kEpiThreads;  // 384
 constexpr int kTmemCols = 512;                  // two 128 x 256 fp32 accumulators (double buffered)
 constexpr uint32_t kIdesc = umma_idesc_f16(128, 256, /*bf16*/ 1);
 
+// Item order: queries (sorted by object) are taken in chunks of kQueryChunk; inside a chunk the template index is the
+// outer loop.  CTAs that run together then share template tiles (queries of one object are adjacent) AND touch at
+// most kQueryChunk query tiles, so both operands stay L2-resident whatever the batch size (at B = 256 with one query
+// per object the plain template-major order re-read every query tile from HBM once per template).
+constexpr int kQueryChunk = 32;
+__device__ __forceinline__ void decode_item(int item, int B, int T, int& j, int& n) {
+  const int per_chunk = kQueryChunk * T;
+  const int c = item / per_chunk, r = item - c * per_chunk;
+  const int q0 = c * kQueryChunk;
+  const int qc = min(kQueryChunk, B - q0);
+  n = r / qc;
+  j = q0 + (r - n * qc);
+}
+
 struct __align__(8) SimSmemTail {
   float smask[kP];                              // template mask sampled at 16x16 (float: alpha masks are not binary)
   float tmask[kP];                              // query mask sampled at 16x16
@@ -114,8 +128,9 @@ sim_search_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
       uint32_t phase = 0;
       const uint32_t tx_bytes = (passes == 3 ? 2 : 1) * (kQPlaneBytes + kTPlaneBytes);
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const int n = item / p.B;
-        const int b = p.perm[item - n * p.B];
+        int j, n;
+        decode_item(item, p.B, p.T, j, n);
+        const int b = p.perm[j];
         const int t_row = (p.q_obj[b] * p.T + n) * kP;
         for (int half = 0; half < 2; ++half) {
           const int q_row = b * kP + half * kHalfRows;
@@ -182,8 +197,9 @@ sim_search_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
     const float thr = p.sim_threshold;
     uint32_t unit = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const int n = item / p.B;
-      const int b = p.perm[item - n * p.B];
+      int j, n;
+      decode_item(item, p.B, p.T, j, n);
+      const int b = p.perm[j];
       const size_t rec = (size_t)b * p.T + n;
       tail.smask[tid] = p.bank_mask[((size_t)p.q_obj[b] * p.T + n) * kP + tid];
       tail.tmask[tid] = p.q_mask[(size_t)b * kP + tid];

@@ -210,7 +210,7 @@ int gp_debug_attention_timeline(long long* stamps32);
 int gp_debug_gemm_timeline(long long* stamps64);
 
 /* test hook: runs the similarity kernel and additionally dumps the raw fp32 similarity tiles, laid out
- * [item = n * B + j][256 t][256 s] where j indexes the queries sorted by object id (small sizes only). */
+ * [item = n * B + j][256 t][256 s] where j indexes the queries sorted by object id (B <= 32, small sizes only). */
 int gp_debug_sim_tiles(gp_handle_t h, int B, float* tiles, void* stream);
 
 #ifdef __cplusplus
