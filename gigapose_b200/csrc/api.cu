@@ -11,6 +11,9 @@
 #include <new>
 #include <string>
 
+int gp_internal_make_map_ex(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows,
+                            int swizzle_bytes);
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -64,21 +67,6 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 plane [rows, 1024] (K contiguous); box = 32 columns (64 B, SWIZZLE_64B) x box_rows rows
-// (256 = all patches of a template, 128 = one t-half of a query)
-int make_plane_map(CUtensorMap* map, void* ptr, uint64_t rows, uint32_t box_rows) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return fail(GP_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from this driver");
-  cuuint64_t dims[2] = {GP_AE_DIM, rows};
-  cuuint64_t strides[1] = {GP_AE_DIM * sizeof(uint16_t)};
-  cuuint32_t box[2] = {32, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(GP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return GP_OK;
-}
-
 }  // namespace
 
 int gp_internal_fail(int code, const char* fmt, ...) {
@@ -91,21 +79,8 @@ int gp_internal_fail(int code, const char* fmt, ...) {
   return code;
 }
 void gp_internal_count_launches(int n) { g_launches += n; }
-// generic 2-D bf16 plane [rows, cols] (cols contiguous), box = 32 columns (SWIZZLE_64B) x box_rows
-int gp_internal_make_map(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return fail(GP_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from this driver");
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * sizeof(uint16_t)};
-  cuuint32_t box[2] = {32, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(GP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return GP_OK;
-}
 
-// generic 2-D bf16 plane map with explicit box and swizzle (swizzle_bytes: 64 or 128 = box_cols * 2)
+// generic 2-D bf16 plane map [rows, cols] (cols contiguous) with explicit box and swizzle (64 or 128 = box_cols * 2 bytes)
 int gp_internal_make_map_ex(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows,
                             int swizzle_bytes) {
   EncodeTiledFn enc = get_encode_fn();
@@ -120,8 +95,19 @@ int gp_internal_make_map_ex(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t
   if (r != CUDA_SUCCESS) return fail(GP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return GP_OK;
 }
+// [rows, cols] plane, box = 32 columns (SWIZZLE_64B) x box_rows
+int gp_internal_make_map(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  return gp_internal_make_map_ex(map, ptr, rows, cols, 32, box_rows, 64);
+}
 
 namespace {
+
+// k-block-tiled bf16 descriptor plane: [image][32 k-blocks][256 patches][32 channels]; seen by TMA as a 2-D array of
+// 64-byte rows [images * 32 * 256, 32]; box = 32 channels (64 B, SWIZZLE_64B) x box_rows patches of one k-block slab
+// (256 = all patches of a template, 128 = one t-half of a query)
+int make_plane_map(CUtensorMap* map, void* ptr, uint64_t images, uint32_t box_rows) {
+  return gp_internal_make_map_ex(map, ptr, images * 32ull * GP_NUM_PATCHES, 32, 32, box_rows, 64);
+}
 
 struct Bank {
   uint16_t *hi, *lo;      // [O*T*256, 1024]
@@ -195,7 +181,7 @@ int validate(const gp_config_t* cfg) {
   if (cfg->patch_size < 1) return fail(GP_ERR_INVALID, "patch_size must be >= 1");
   if (cfg->precision != GP_PRECISION_FP32_SPLIT && cfg->precision != GP_PRECISION_BF16)
     return fail(GP_ERR_INVALID, "unknown precision %d", cfg->precision);
-  if ((size_t)cfg->num_objects * cfg->num_templates * GP_NUM_PATCHES >= (1ull << 31))
+  if ((size_t)cfg->num_objects * cfg->num_templates * GP_NUM_PATCHES * 32 >= (1ull << 31))
     return fail(GP_ERR_INVALID, "bank has too many rows for 32-bit TMA coordinates");
   return GP_OK;
 }
@@ -252,8 +238,8 @@ int gp_create(const gp_config_t* cfg, void* bank_mem, void* workspace_mem, gp_ha
   Carver cb(bank_mem), cw(workspace_mem);
   carve_bank(cb, *cfg, &h->bank);
   carve_workspace(cw, *cfg, &h->ws);
-  const uint64_t bank_rows = (uint64_t)cfg->num_objects * cfg->num_templates * GP_NUM_PATCHES;
-  const uint64_t q_rows = (uint64_t)cfg->max_batch * GP_NUM_PATCHES;
+  const uint64_t bank_rows = (uint64_t)cfg->num_objects * cfg->num_templates;   // images
+  const uint64_t q_rows = (uint64_t)cfg->max_batch;
   int e;
   if ((e = make_plane_map(&h->tm_t_hi, h->bank.hi, bank_rows, 256)) || (e = make_plane_map(&h->tm_t_lo, h->bank.lo, bank_rows, 256)) ||
       (e = make_plane_map(&h->tm_q_hi, h->ws.q_hi, q_rows, 128)) || (e = make_plane_map(&h->tm_q_lo, h->ws.q_lo, q_rows, 128))) {
@@ -285,10 +271,10 @@ int gp_bank_write(gp_handle_t h, int obj, int tmpl0, int n, const float* feat, i
   const size_t plane_off = slot * GP_NUM_PATCHES * GP_AE_DIM;
   const long long img_stride = (long long)GP_NUM_PATCHES * GP_AE_DIM;
   if (feat_layout == GP_LAYOUT_CHANNEL_MAJOR)
-    GP_CUDA(gp::launch_split_descriptors(feat, rows, GP_AE_DIM, GP_NUM_PATCHES, img_stride, 1, GP_NUM_PATCHES, norm_passes,
+    GP_CUDA(gp::launch_split_descriptors(feat, rows, GP_AE_DIM, GP_NUM_PATCHES, img_stride, 1, GP_NUM_PATCHES, norm_passes, 1,
                                          h->bank.hi + plane_off, h->bank.lo + plane_off, nullptr, s));
   else if (feat_layout == GP_LAYOUT_PATCH_MAJOR)
-    GP_CUDA(gp::launch_split_descriptors(feat, rows, GP_AE_DIM, GP_NUM_PATCHES, img_stride, GP_AE_DIM, 1, norm_passes,
+    GP_CUDA(gp::launch_split_descriptors(feat, rows, GP_AE_DIM, GP_NUM_PATCHES, img_stride, GP_AE_DIM, 1, norm_passes, 1,
                                          h->bank.hi + plane_off, h->bank.lo + plane_off, nullptr, s));
   else
     return fail(GP_ERR_INVALID, "unknown feature layout %d", feat_layout);
@@ -334,10 +320,10 @@ int gp_set_queries(gp_handle_t h, int B, const float* q_feat, int feat_layout, i
   const long long rows = (long long)B * GP_NUM_PATCHES;
   const long long img_stride = (long long)GP_NUM_PATCHES * GP_AE_DIM;
   if (feat_layout == GP_LAYOUT_CHANNEL_MAJOR)
-    GP_CUDA(gp::launch_split_descriptors(q_feat, rows, GP_AE_DIM, GP_NUM_PATCHES, img_stride, 1, GP_NUM_PATCHES, norm_passes,
+    GP_CUDA(gp::launch_split_descriptors(q_feat, rows, GP_AE_DIM, GP_NUM_PATCHES, img_stride, 1, GP_NUM_PATCHES, norm_passes, 1,
                                          h->ws.q_hi, h->ws.q_lo, nullptr, s));
   else if (feat_layout == GP_LAYOUT_PATCH_MAJOR)
-    GP_CUDA(gp::launch_split_descriptors(q_feat, rows, GP_AE_DIM, GP_NUM_PATCHES, img_stride, GP_AE_DIM, 1, norm_passes,
+    GP_CUDA(gp::launch_split_descriptors(q_feat, rows, GP_AE_DIM, GP_NUM_PATCHES, img_stride, GP_AE_DIM, 1, norm_passes, 1,
                                          h->ws.q_hi, h->ws.q_lo, nullptr, s));
   else
     return fail(GP_ERR_INVALID, "unknown feature layout %d", feat_layout);

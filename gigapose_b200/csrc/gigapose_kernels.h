@@ -69,6 +69,7 @@ cudaError_t launch_topk_merge_expand(const TopkMergeParams& p, cudaStream_t stre
 // (F.normalize semantics, eps 1e-12) and writes the bf16 hi / lo planes [n_rows, C].
 cudaError_t launch_split_descriptors(const float* x, long long n_rows, int C, int rows_per_img, long long img_stride,
                                      long long row_stride, long long chan_stride, int norm_passes,
+                                     int tiled /*1: [img][C/32][rows_per_img][32] k-block-tiled planes*/,
                                      uint16_t* hi, uint16_t* lo, float* normalized_out /*nullable [n_rows,C]*/,
                                      cudaStream_t stream);
 // nearest-neighbour H x W -> 16 x 16 sampling of float masks (F.interpolate default mode), [n,H,W] -> [n,256]

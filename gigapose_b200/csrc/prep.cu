@@ -30,8 +30,8 @@ constexpr int kMaxPerThread = 8;
 
 __global__ void __launch_bounds__(256)
 split_descriptors_kernel(const float* __restrict__ x, long long n_rows, int C, int rows_per_img, long long img_stride,
-                         long long row_stride, long long chan_stride, int norm_passes, __nv_bfloat16* __restrict__ hi,
-                         __nv_bfloat16* __restrict__ lo, float* __restrict__ normalized_out) {
+                         long long row_stride, long long chan_stride, int norm_passes, int tiled,
+                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ normalized_out) {
   __shared__ float s_red[8];
   const long long r = blockIdx.x;
   if (r >= n_rows) return;
@@ -57,8 +57,12 @@ split_descriptors_kernel(const float* __restrict__ x, long long n_rows, int C, i
     if (i < per && c < C) {
       const __nv_bfloat16 h = __float2bfloat16_rn(v[i]);
       const __nv_bfloat16 l = __float2bfloat16_rn(v[i] - __bfloat162float(h));
-      hi[r * C + c] = h;
-      lo[r * C + c] = l;
+      // k-block-tiled planes: [image][c / 32][patch][c % 32] -- the 256 x 32 box the similarity kernel's TMA fetches
+      // per K-block is one contiguous 16 KB slab (streams from HBM at full page locality when nothing is shared)
+      const size_t o = tiled ? ((((size_t)(r / rows_per_img) * (C / 32) + (c >> 5)) * rows_per_img + (r % rows_per_img)) << 5) + (c & 31)
+                             : (size_t)r * C + c;
+      hi[o] = h;
+      lo[o] = l;
       if (normalized_out) normalized_out[r * C + c] = v[i];
     }
   }
@@ -116,12 +120,12 @@ cudaError_t launch_object_order(const int* q_obj, int B, int num_objects, int* p
 }
 
 cudaError_t launch_split_descriptors(const float* x, long long n_rows, int C, int rows_per_img, long long img_stride,
-                                     long long row_stride, long long chan_stride, int norm_passes, uint16_t* hi,
+                                     long long row_stride, long long chan_stride, int norm_passes, int tiled, uint16_t* hi,
                                      uint16_t* lo, float* normalized_out, cudaStream_t stream) {
   if (n_rows <= 0) return cudaSuccess;
   if (C > 256 * kMaxPerThread) return cudaErrorInvalidValue;
   split_descriptors_kernel<<<(unsigned)n_rows, 256, 0, stream>>>(x, n_rows, C, rows_per_img, img_stride, row_stride,
-                                                                chan_stride, norm_passes,
+                                                                chan_stride, norm_passes, tiled,
                                                                 reinterpret_cast<__nv_bfloat16*>(hi),
                                                                 reinterpret_cast<__nv_bfloat16*>(lo), normalized_out);
   return cudaGetLastError();

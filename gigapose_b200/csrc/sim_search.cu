@@ -131,18 +131,20 @@ sim_search_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
         int j, n;
         decode_item(item, p.B, p.T, j, n);
         const int b = p.perm[j];
-        const int t_row = (p.q_obj[b] * p.T + n) * kP;
+        const int t_img = p.q_obj[b] * p.T + n;
         for (int half = 0; half < 2; ++half) {
-          const int q_row = b * kP + half * kHalfRows;
           for (int kb = 0; kb < kNumKBlocks; ++kb) {
             mbar_wait(&tail.empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * kStageBytes;
             mbar_arrive_expect_tx(&tail.full_bar[stage], tx_bytes);
-            tma_load_2d(st, &tm_q_hi, &tail.full_bar[stage], kb * kBlockK, q_row);
-            tma_load_2d(st + 2 * kQPlaneBytes, &tm_t_hi, &tail.full_bar[stage], kb * kBlockK, t_row);
+            // k-block-tiled planes: slab (image, kb) = 256 contiguous 64-byte rows
+            const int q_row = (b * kNumKBlocks + kb) * kP + half * kHalfRows;
+            const int t_row = (t_img * kNumKBlocks + kb) * kP;
+            tma_load_2d(st, &tm_q_hi, &tail.full_bar[stage], 0, q_row);
+            tma_load_2d(st + 2 * kQPlaneBytes, &tm_t_hi, &tail.full_bar[stage], 0, t_row);
             if (passes == 3) {
-              tma_load_2d(st + 2 * kQPlaneBytes + kTPlaneBytes, &tm_t_lo, &tail.full_bar[stage], kb * kBlockK, t_row);
-              tma_load_2d(st + kQPlaneBytes, &tm_q_lo, &tail.full_bar[stage], kb * kBlockK, q_row);
+              tma_load_2d(st + 2 * kQPlaneBytes + kTPlaneBytes, &tm_t_lo, &tail.full_bar[stage], 0, t_row);
+              tma_load_2d(st + kQPlaneBytes, &tm_q_lo, &tail.full_bar[stage], 0, q_row);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
