@@ -256,6 +256,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="launch the per-batch kernel sequence eagerly")
     ap.add_argument("--profile-range", action="store_true",
                     help="wrap ONE extra resident step in cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -301,6 +302,7 @@ def main():
 
     from gigapose_b200 import vit_engine
     model = build_models(device)
+    model.use_cuda_graph = not args.no_cuda_graph and not args.profile_range
     templates = SyntheticTemplates(cfg["O"], cfg["T"], device)
     model.template_datasets = {"synthetic": templates}
     model.test_dataset_name = "synthetic"
@@ -317,10 +319,16 @@ def main():
         pred = model.retrieve(batch_host, "synthetic")          # H2D of crops/masks/K/M happens inside
         return pred.pred_poses.cpu(), pred.scores.cpu()           # D2H of the step's result
 
+    # kernel launches of THIS library per step, counted on one eager step (a graph replay re-issues the same kernels
+    # without going through the C entry points that keep the counter)
+    graph_flag, model.use_cuda_graph = model.use_cuda_graph, False
+    l0 = eng.launch_count()
+    step_resident()
+    launches = eng.launch_count() - l0
+    model.use_cuda_graph = graph_flag
     for _ in range(args.warmup):
         step_resident()
     torch.cuda.synchronize()
-    l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         torch.cuda.synchronize()
@@ -330,7 +338,6 @@ def main():
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
-    launches = (eng.launch_count() - l0) // args.steps
     value = cfg["B"] / (ms / 1e3)
 
     # per-stage CUDA-event times of one extra resident step (diagnostic, outside the timed region)
@@ -399,6 +406,7 @@ def main():
             "e2e": {"value": cfg["B"] / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
             "gpu_launches": int(launches), "roofline": roofline, "stage_ms": stage_ms}
+    line["config"]["cuda_graph"] = bool(model.use_cuda_graph)
     if not args.no_cpu_baseline:
         v, info = cpu_reference_rate(cfg, sample_dets=8, reps=2)
         line["cpu_baseline"] = dict(value=v, unit=UNIT, **info)

@@ -133,7 +133,10 @@ sim_search_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
         const int b = p.perm[j];
         const int t_img = p.q_obj[b] * p.T + n;
         for (int half = 0; half < 2; ++half) {
-          for (int kb = 0; kb < kNumKBlocks; ++kb) {
+          for (int kbi = 0; kbi < kNumKBlocks; ++kbi) {
+            // the second t-half walks K backwards: the template slabs it needs first are the ones the first half
+            // touched last, i.e. the ones most likely still in L2 when nothing else shares the template (B_o = 1)
+            const int kb = half == 0 ? kbi : kNumKBlocks - 1 - kbi;
             mbar_wait(&tail.empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * kStageBytes;
             mbar_arrive_expect_tx(&tail.full_bar[stage], tx_bytes);
