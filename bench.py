@@ -30,6 +30,18 @@ import numpy as np  # noqa: E402
 import pandas as pd  # noqa: E402
 import torch  # noqa: E402
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 WORKLOADS = {
     # name: (objects, templates, batch)  -- BASELINE.json configs[1..4]
     "c1": dict(O=1, T=16, B=1, desc="single query vs 16 templates (CPU-runnable plumbing case)"),
@@ -261,6 +273,12 @@ def main():
                     help="wrap ONE extra resident step in cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
 
+    # stdout carries exactly ONE JSON line: libraries (NCCL's version banner, cuDNN logs) write to fd 1 too, so the
+    # real stdout is kept aside and fd 1 points at stderr until the line is printed
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -285,7 +303,7 @@ def main():
                 "cpu_baseline": dict(value=value, unit=UNIT, **info),
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     assert torch.cuda.is_available(), "bench.py (impl=ours) needs a CUDA device: there is no CPU fallback"
@@ -298,7 +316,7 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     if world > 1:
         from gigapose_b200.multigpu import run_sharded_bench
-        return run_sharded_bench(args, cfg, config, wl_name, rank, world, device, METRIC, UNIT, ClockSampler)
+        return run_sharded_bench(args, cfg, config, wl_name, rank, world, device, METRIC, UNIT, ClockSampler, emit)
 
     from gigapose_b200 import vit_engine
     model = build_models(device)
@@ -410,7 +428,7 @@ def main():
     if not args.no_cpu_baseline:
         v, info = cpu_reference_rate(cfg, sample_dets=8, reps=2)
         line["cpu_baseline"] = dict(value=v, unit=UNIT, **info)
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 

@@ -171,7 +171,7 @@ class ShardedRetriever:
         return eng.sort_and_pose(tar_K, tar_M, m, rel_scale, rel_inplane, rr)
 
 
-def run_sharded_bench(args, cfg, config, wl_name, rank, world, device, METRIC, UNIT, ClockSampler):
+def run_sharded_bench(args, cfg, config, wl_name, rank, world, device, METRIC, UNIT, ClockSampler, emit):
     """bench.py body for N > 1 (launched by torch.distributed.run, one rank per GPU)."""
     import bench
     from . import vit_engine
@@ -255,7 +255,7 @@ def run_sharded_bench(args, cfg, config, wl_name, rank, world, device, METRIC, U
                 "roofline": {"bound": "tensor", "kernel": "sim_search_kernel", "achieved": achieved, "peak": peak_tf,
                              "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "ms_per_launch": float(sim_t),
                              "note": "per-GPU: each rank runs all B queries against its 1/N template shard"}}
-        print(json.dumps(line))
+        emit(line)
     dist.barrier()
     dist.destroy_process_group()
     return 0
