@@ -81,9 +81,15 @@ def load():
     sys.modules.update(stubs)
     old_path = list(sys.path)
     sys.path[:0] = [REF_ROOT, os.path.join(REF_ROOT, "src")]
+    # The reference's `src` is a namespace package (no __init__.py) while this repository's `src` is a regular one,
+    # and regular packages win regardless of sys.path order: pin `src` to the reference directory explicitly.
+    ref_src = types.ModuleType("src")
+    ref_src.__path__ = [os.path.join(REF_ROOT, "src")]
+    sys.modules["src"] = ref_src
     try:
         ns = types.SimpleNamespace()
         m = importlib.import_module("src.models.matching")
+        assert os.path.realpath(m.__file__).startswith(os.path.realpath(REF_ROOT)), m.__file__
         ns.LocalSimilarity = m.LocalSimilarity
         m = importlib.import_module("src.models.ransac")
         ns.RANSAC = m.RANSAC
