@@ -233,29 +233,64 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # CPU reference arm: the oracle port (the reference modules cannot travel to the GPU box) on all host threads
 # ----------------------------------------------------------------------------------------------------------------
+_CPU_THREADS = None
+_CPU_CTX = {}
+
+
+def _pick_cpu_threads(run_once):
+    """More threads are not always faster for the reference's many small ops (128 threads were measured 20x slower
+    than 8 on this path): time one tiny run at a few thread counts and keep the best."""
+    global _CPU_THREADS
+    if _CPU_THREADS is not None:
+        return _CPU_THREADS
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        run_once()                                  # warm
+        t0 = time.perf_counter()
+        run_once()
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    _CPU_THREADS = best
+    return best
+
+
 def cpu_reference_rate(cfg, sample_dets=2, reps=1, threads=None):
     """Times the CPU restatement of the reference path (oracle/port.py, pinned against the unmodified reference by
     tests/golden) on a bounded sample: `sample_dets` detections of one object against its full T-template bank.
     Returns detections/s.  Includes a1 (ViT) + a4 + a6 (once, the "fair" variant) + a5 + a7-a9."""
     from gigapose_b200 import synth
     from oracle import port
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
     T = cfg["T"]
-    case = synth.make_feature_case(B=sample_dets, O=1, T=T, seed=77)
-    ri = synth.to_reference_layout(case)
-    vit, backbone, reg = port.DinoV2Port(), port.ISTBackbonePort(), port.RegressorPort()
-    rgb, _ = synth.make_crops(sample_dets, seed=78)
+    key = (T, sample_dets)
+    if key not in _CPU_CTX:                         # models + inputs are built once per process
+        _CPU_CTX.clear()
+        case = synth.make_feature_case(B=sample_dets, O=1, T=T, seed=77)
+        _CPU_CTX[key] = (synth.to_reference_layout(case), port.DinoV2Port(), port.ISTBackbonePort(), port.RegressorPort(),
+                         synth.make_crops(sample_dets, seed=78)[0])
+    ri, vit, backbone, reg, rgb = _CPU_CTX[key]
+
+    def run(n=sample_dets):
+        _ = port.ae_features(vit, rgb[:n])          # a1 on the query crops
+        _ = backbone(rgb[:n])                       # a6 once per crop
+        sub = {k: (v[:n] if k in ("src_feats", "tar_feat", "src_masks", "tar_mask", "src_ist", "tar_ist", "tar_label",
+                                  "tar_K", "tar_M") else v) for k, v in ri.items()}
+        _ = port.retrieval(sub, reg)                # a4, a5, a7, a8, a9 on planted features of the same shape
+
+    threads = threads or _pick_cpu_threads(lambda: run(1))
+    torch.set_num_threads(threads)
     times = []
     for _ in range(reps + 1):                       # first repetition = warm-up
         t0 = time.perf_counter()
-        _ = port.ae_features(vit, rgb)              # a1 on the query crops
-        _ = backbone(rgb)                           # a6 once per crop
-        _ = port.retrieval(ri, reg)                 # a4, a5, a7, a8, a9 on planted features of the same shape
+        run()
         times.append(time.perf_counter() - t0)
     best = min(times[1:]) if len(times) > 1 else times[0]
     return sample_dets / best, dict(cores=threads, kind="port",
-                                    sample=f"{sample_dets} detections vs 1 object x {T} templates, fp32 torch CPU, "
+                                    sample=f"{sample_dets} detections vs 1 object x {T} templates, fp32 torch CPU "
+                                           f"({threads} of {os.cpu_count()} host threads: fastest of a short sweep), "
                                            f"ViT-L/14 + IST backbone once + similarity/MLP/RANSAC/pose, best of {reps}")
 
 
@@ -290,15 +325,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        vals = []
-        info = None
-        for _ in range(max(1, args.warmup > 0) + args.steps):
-            v, info = cpu_reference_rate(cfg, sample_dets=8, reps=1)
-            vals.append(v)
-        vals = vals[1:] if len(vals) > args.steps else vals
+        vals, info = [], None
+        for i in range(min(args.warmup, 1) + args.steps):     # each step = a bounded 2-detection sample (~seconds)
+            v, info = cpu_reference_rate(cfg, sample_dets=2, reps=1)
+            if i >= min(args.warmup, 1):
+                vals.append(v)
         value = statistics.mean(vals)
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * 8 / value, "higher_is_better": True,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * 2 / value, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": dict(value=value, unit=UNIT, **info),
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -426,7 +460,7 @@ def main():
             "gpu_launches": int(launches), "roofline": roofline, "stage_ms": stage_ms}
     line["config"]["cuda_graph"] = bool(model.use_cuda_graph)
     if not args.no_cpu_baseline:
-        v, info = cpu_reference_rate(cfg, sample_dets=8, reps=2)
+        v, info = cpu_reference_rate(cfg, sample_dets=4, reps=2)
         line["cpu_baseline"] = dict(value=v, unit=UNIT, **info)
     emit(line)
     return 0

@@ -40,7 +40,11 @@ def _params_in_abi_order(m, device):
 
 
 def _version_key(m):
-    return sum(int(p._version) for p in m.parameters()) + sum(p.data_ptr() & 0xFFFF for p in m.parameters())
+    """Cheap staleness key: the packed GEMM planes must be rebuilt when the module's parameters are replaced
+    (`.to()`, `load_state_dict`) or modified in place.  A handful of tensors is enough to notice all of those."""
+    probes = (m.cls_token, m.pos_embed, m.patch_embed.proj.weight, m.blocks[0].attn.qkv.weight, m.blocks[-1].mlp.fc2.weight,
+              m.blocks[-1].ls2.gamma)
+    return tuple((p.data_ptr(), int(p._version)) for p in probes)
 
 
 class NativeViT:
