@@ -146,3 +146,39 @@ def test_ist_backbone_matches_oracle(golden_dir):
     want = torch.from_numpy(g["ist_feat_sub"])
     scale = want.abs().max().item()
     assert (got[:, ::2] - want).abs().max().item() < 3e-3 * scale
+
+
+def test_test_step_writes_reference_npz_schema(tmp_path):
+    """`test_step` with a `test_list` (localisation setting): per-object top-`inst_count` filtering by the best
+    hypothesis score and the per-image .npz the reference writes (gigaPose.py:400-449)."""
+    import os
+    import sys
+    import numpy as np
+    import pandas as pd
+    import src.megapose.utils.tensor_collection as tc
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    model = bench.build_models(torch.device(DEV))
+    model.log_dir = str(tmp_path)
+    os.makedirs(os.path.join(model.log_dir, "predictions"), exist_ok=True)
+    templates = bench.SyntheticTemplates(2, 8, torch.device(DEV))
+    model.template_datasets = {"synthetic": templates}
+    model.test_dataset_name = "synthetic"
+    batch, labels, views = bench.make_queries(templates, 5, seed=4)
+    obj_ids = sorted(set(int(l) for l in labels))
+    test_list = tc.PandasTensorCollection(infos=pd.DataFrame(dict(obj_id=obj_ids, inst_count=[1] * len(obj_ids),
+                                                                  detection_time=[0.25] * len(obj_ids))))
+    batch.register_tensor("test_list", test_list)
+    assert model.test_step(batch, 7) == 0
+    data = np.load(os.path.join(model.log_dir, "predictions", "7.npz"))
+    assert set(data.files) == {"scene_id", "im_id", "object_id", "time", "detection_time", "poses", "scores"}
+    n = len(obj_ids)                                   # one instance kept per object
+    assert data["poses"].shape == (n, 5, 4, 4) and data["scores"].shape == (n, 5)
+    assert sorted(data["object_id"].tolist()) == obj_ids
+    assert np.allclose(data["detection_time"], 0.25) and (data["time"] > 0).all()
+    # the kept detection of each object is the one with the highest top-1 score among that object's detections
+    pred = model.retrieve(batch, "synthetic")
+    s0 = pred.scores[:, 0].cpu().numpy()
+    lab = labels.numpy()
+    for row, oid in enumerate(data["object_id"]):
+        assert np.isclose(data["scores"][row, 0], s0[lab == oid].max())
