@@ -11,6 +11,8 @@
 #include <new>
 #include <string>
 
+int gp_internal_make_map_nhwc(CUtensorMap* map, void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint32_t out_w,
+                              uint32_t out_h, uint32_t stride);
 int gp_internal_make_map_ex(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows,
                             int swizzle_bytes);
 
@@ -93,6 +95,22 @@ int gp_internal_make_map_ex(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(GP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return GP_OK;
+}
+// NHWC bf16 plane [N, H, W, C] as a 4-D tensor {C, W, H, N}; box = 32 channels x out_w x out_h output positions taken
+// with element stride `stride` along x and y (the traversal box spans out * stride input elements).  Coordinates that
+// fall outside [0,W) x [0,H) -- the zero padding of a convolution -- are filled with zeros by TMA.
+int gp_internal_make_map_nhwc(CUtensorMap* map, void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint32_t out_w,
+                              uint32_t out_h, uint32_t stride) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(GP_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from this driver");
+  cuuint64_t dims[4] = {C, W, H, N};
+  cuuint64_t strides[3] = {C * sizeof(uint16_t), W * C * sizeof(uint16_t), H * W * C * sizeof(uint16_t)};
+  cuuint32_t box[4] = {32, out_w * stride, out_h * stride, 1};
+  cuuint32_t estr[4] = {1, stride, stride, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GP_ERR_CUDA, "cuTensorMapEncodeTiled (NHWC) failed with CUresult %d", (int)r);
   return GP_OK;
 }
 // [rows, cols] plane, box = 32 columns (SWIZZLE_64B) x box_rows

@@ -153,7 +153,8 @@ cudaError_t launch_pose_only(int n, int k, int T, const int* q_obj, const float*
                              const float* tmpl_pose, float* poses, cudaStream_t stream);
 
 // ---------------------------------------------------------------- ViT-L/14 (vit_gemm.cu, vit_ops.cu)
-enum GemmMode { GEMM_PLANES = 0, GEMM_PLANES_GELU = 1, GEMM_SCALE_RESIDUAL = 2, GEMM_PATCH_EMBED = 3, GEMM_QKV_HEADS = 4 };
+enum GemmMode { GEMM_PLANES = 0, GEMM_PLANES_GELU = 1, GEMM_SCALE_RESIDUAL = 2, GEMM_PATCH_EMBED = 3, GEMM_QKV_HEADS = 4,
+                GEMM_PLANES_RELU = 5, GEMM_PLANES_ADD_RELU = 6, GEMM_ROWS_F32 = 7 };
 struct GemmParams {
   int M, N, K;                // C[M,N] = A[M,K] W[N,K]^T ; N % 256 == 0, K % 32 == 0
   int passes;                 // 3 = hi*hi + hi*lo + lo*hi, 1 = hi*hi
@@ -165,6 +166,11 @@ struct GemmParams {
   const float* pos;           // [257,N] positional table (GEMM_PATCH_EMBED)
   int tokens_per_img, patches_per_img;
   int qkv_crop_stride;        // GEMM_QKV_HEADS: crops per q/k/v section of the head-major planes (= max_crops)
+  int bn;                     // output-tile width: 128, 192 or 256 (0 = 256); N % bn == 0
+  // implicit-GEMM convolution (conv != 0): A is an NHWC plane read through a 4-D tensor map, one k-block per
+  // (filter tap, 32-channel block); a 128-row tile is 128 / Wo whole output rows of one image
+  int conv, Ho, Wo, stride, pad, kw, cblocks;
+  const uint16_t *res_hi, *res_lo;   // GEMM_PLANES_ADD_RELU: shortcut planes [M,N]
 };
 cudaError_t launch_vit_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                             const CUtensorMap& w_lo, const GemmParams& p, int num_sms, cudaStream_t stream);

@@ -1,0 +1,282 @@
+// Native IST trunk (rows a6 / f1 of SURVEY.md §8): the ResNet the reference runs at ist_net.py:62-63 through
+// src/models/network/resnet.py:318-381 (bilinear 224 -> 256, 7x7/2 stem, four stages of two BasicBlocks with dims
+// 128/192/256/512, 1x1 output convolution to 256 channels at 1/16 resolution), inference form: BatchNorm folded into
+// the convolution weights by the caller.
+//
+// Every convolution is an implicit GEMM on the same tcgen05 kernel as the ViT linears (vit_gemm.cu): activations are
+// NHWC bf16 hi/lo planes, one output tile = 128 consecutive output pixels (whole output rows of one image) x all / half
+// of the output channels, and the A operand of k-block (ky, kx, 32-channel block) is fetched by ONE 4-D TMA box per
+// plane -- a shifted, strided window of the input plane whose out-of-image part TMA zero-fills (the padding).  No
+// im2col buffer exists except for the 3-channel stem (K = 7*7*3 = 147 -> 160 columns), which also fuses the resize.
+// ReLU, the residual add and the hi/lo split of the next layer's input are the GEMM epilogue.
+#include "../../include/gigapose_b200.h"
+#include "gigapose_kernels.h"
+
+#include <cuda_bf16.h>
+#include <new>
+#include <vector>
+
+extern int gp_internal_fail(int code, const char* fmt, ...);
+extern void gp_internal_count_launches(int n);
+extern int gp_internal_make_map(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
+extern int gp_internal_make_map_nhwc(CUtensorMap* map, void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t N,
+                                     uint32_t out_w, uint32_t out_h, uint32_t stride);
+
+namespace {
+
+constexpr int kIn = 224, kRes = 256, kStemOut = 128, kStemK = 147, kStemKPad = 160, kFeat = 256;
+constexpr int kDims[4] = {128, 192, 256, 512};
+constexpr int kNumConvs = GP_IST_TRUNK_NUM_CONVS;
+constexpr size_t kAlign = 1024;
+inline size_t up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+
+struct Carver {
+  uint8_t* base; size_t off = 0;
+  explicit Carver(void* b) : base(static_cast<uint8_t*>(b)) {}
+  template <typename T> T* take(size_t n) { T* p = base ? reinterpret_cast<T*>(base + off) : nullptr; off += up(n * sizeof(T)); return p; }
+};
+
+struct Planes { uint16_t *hi = nullptr, *lo = nullptr; };
+
+struct Conv {
+  int cin, cout, k, stride, pad, hin, hout;     // square maps and filters
+  int K, Kpad, bn, mode;
+  int in_buf, out_buf, res_buf;                 // activation buffers (-1: stem im2col planes / none)
+  Planes w;
+  const float* bias;
+  CUtensorMap a_hi, a_lo, w_hi, w_lo;
+};
+
+// The 21 convolutions in ABI (= execution) order: stem; per BasicBlock conv1, [downsample,] conv2; output convolution.
+std::vector<Conv> make_schedule() {
+  std::vector<Conv> v;
+  auto add = [&](int cin, int cout, int k, int stride, int pad, int hin, int mode, int in_buf, int out_buf, int res_buf) {
+    Conv c{};
+    c.cin = cin; c.cout = cout; c.k = k; c.stride = stride; c.pad = pad; c.hin = hin; c.hout = hin / stride;
+    c.K = k * k * cin; c.Kpad = (c.K + 31) / 32 * 32;
+    c.bn = cout == 128 ? 128 : (cout == 192 ? 192 : 256);
+    c.mode = mode; c.in_buf = in_buf; c.out_buf = out_buf; c.res_buf = res_buf;
+    v.push_back(c);
+  };
+  add(3, kStemOut, 7, 2, 3, kRes, gp::GEMM_PLANES_RELU, -1, 0, -1);
+  int x = 0, width = kStemOut, h = kStemOut;
+  for (int st = 0; st < 4; ++st) {
+    const int d = kDims[st];
+    for (int blk = 0; blk < 2; ++blk) {
+      const int stride = (blk == 0 && st > 0) ? 2 : 1;
+      int free_buf[3], nf = 0;
+      for (int b = 0; b < 4; ++b) if (b != x) free_buf[nf++] = b;
+      const int y = free_buf[0];
+      const bool ds = stride != 1;
+      const int res = ds ? free_buf[1] : x, z = ds ? free_buf[2] : free_buf[1];
+      add(width, d, 3, stride, 1, h, gp::GEMM_PLANES_RELU, x, y, -1);                 // relu(bn1(conv1 x))   resnet.py:45
+      if (ds) add(width, d, 1, stride, 0, h, gp::GEMM_PLANES, x, res, -1);           // downsample: 1x1/2 conv + bn
+      add(d, d, 3, 1, 1, h / stride, gp::GEMM_PLANES_ADD_RELU, y, z, res);            // relu(shortcut + bn2(conv2 .))
+      x = z; width = d; h /= stride;
+    }
+  }
+  add(kDims[3], kFeat, 1, 1, 0, h, gp::GEMM_ROWS_F32, x, -1, -1);                     // layer4_outconv   resnet.py:379
+  return v;
+}
+
+#define GPI_CUDA(expr)                                                                                    \
+  do {                                                                                                    \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess) return gp_internal_fail(GP_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+__device__ __forceinline__ void split_store(float v, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t i) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = h;
+  lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// Bilinear 224 -> 256 (align_corners=True, resnet.py:365-368) fused with the stem's im2col:
+// planes[(img*128 + yo)*128 + xo][(ky*7 + kx)*3 + c] = resized[img][c][2*yo + ky - 3][2*xo + kx - 3]  (0 outside).
+__global__ void stem_im2col_kernel(const float* __restrict__ img, int n, __nv_bfloat16* __restrict__ hi,
+                                   __nv_bfloat16* __restrict__ lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n * kStemOut * kStemOut * kStemKPad;
+  if (i >= total) return;
+  const long long row = i / kStemKPad;
+  const int k = (int)(i - row * kStemKPad);
+  float v = 0.f;
+  if (k < kStemK) {
+    const int im = (int)(row / (kStemOut * kStemOut)), pix = (int)(row - (long long)im * kStemOut * kStemOut);
+    const int yo = pix / kStemOut, xo = pix - yo * kStemOut;
+    const int tap = k / 3, c = k - tap * 3, ky = tap / 7, kx = tap - ky * 7;
+    const int y = 2 * yo + ky - 3, x = 2 * xo + kx - 3;
+    if (y >= 0 && y < kRes && x >= 0 && x < kRes) {
+      const float scale = (float)(kIn - 1) / (float)(kRes - 1);
+      const float fy = scale * y, fx = scale * x;
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int yp = y0 < kIn - 1 ? 1 : 0, xp = x0 < kIn - 1 ? 1 : 0;
+      const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+      const float* src = img + ((size_t)im * 3 + c) * kIn * kIn;
+      v = hy * (hx * src[y0 * kIn + x0] + lx * src[y0 * kIn + x0 + xp]) +
+          ly * (hx * src[(y0 + yp) * kIn + x0] + lx * src[(y0 + yp) * kIn + x0 + xp]);
+    }
+  }
+  split_store(v, hi, lo, (size_t)i);
+}
+
+__global__ void merge_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, long long n,
+                                    float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
+}
+
+}  // namespace
+
+struct gp_ist_trunk_context {
+  int max_crops, passes, num_sms;
+  std::vector<Conv> convs;
+  Planes act[4];               // NHWC activation planes, each sized for the largest map [max_crops,128,128,128]
+  Planes stem;                 // [max_crops*128*128, 160] im2col planes of the resized crop
+  const float* zero_bias;      // [512] zeros (the output convolution has no bias)
+};
+
+namespace {
+
+void carve_weights(Carver& c, gp_ist_trunk_context* h, const std::vector<Conv>& sched) {
+  for (size_t i = 0; i < sched.size(); ++i) {
+    const size_t n = (size_t)sched[i].cout * sched[i].Kpad;
+    uint16_t* a = c.take<uint16_t>(n); uint16_t* b = c.take<uint16_t>(n);
+    if (h) { h->convs[i].w.hi = a; h->convs[i].w.lo = b; }
+  }
+  const float* z = c.take<float>(512);
+  if (h) h->zero_bias = z;
+}
+
+void carve_workspace(Carver& c, int max_crops, gp_ist_trunk_context* h) {
+  const size_t act = (size_t)max_crops * kStemOut * kStemOut * kDims[0];
+  for (int b = 0; b < 4; ++b) {
+    uint16_t* a = c.take<uint16_t>(act); uint16_t* l = c.take<uint16_t>(act);
+    if (h) { h->act[b].hi = a; h->act[b].lo = l; }
+  }
+  const size_t st = (size_t)max_crops * kStemOut * kStemOut * kStemKPad;
+  uint16_t* a = c.take<uint16_t>(st); uint16_t* l = c.take<uint16_t>(st);
+  if (h) { h->stem.hi = a; h->stem.lo = l; }
+}
+
+int run(gp_ist_trunk_context* h, int n, const float* crops, float* feat, int stop_after, float* dump, cudaStream_t s) {
+  const long long stem_total = (long long)n * kStemOut * kStemOut * kStemKPad;
+  stem_im2col_kernel<<<(unsigned)((stem_total + 255) / 256), 256, 0, s>>>(
+      crops, n, reinterpret_cast<__nv_bfloat16*>(h->stem.hi), reinterpret_cast<__nv_bfloat16*>(h->stem.lo));
+  GPI_CUDA(cudaGetLastError());
+  int launched = 1;
+  const int last = stop_after > 0 && stop_after < (int)h->convs.size() ? stop_after : (int)h->convs.size();
+  for (int i = 0; i < last; ++i) {
+    const Conv& c = h->convs[i];
+    gp::GemmParams g{};
+    g.passes = h->passes; g.mode = c.mode; g.bn = c.bn;
+    g.M = n * c.hout * c.hout; g.N = c.cout; g.K = c.Kpad;
+    g.bias = c.bias ? c.bias : h->zero_bias;
+    if (c.out_buf >= 0) { g.out_hi = h->act[c.out_buf].hi; g.out_lo = h->act[c.out_buf].lo; }
+    else g.x = feat;
+    if (c.res_buf >= 0) { g.res_hi = h->act[c.res_buf].hi; g.res_lo = h->act[c.res_buf].lo; }
+    if (c.in_buf >= 0 && !(c.k == 1 && c.stride == 1)) {
+      g.conv = 1; g.Ho = c.hout; g.Wo = c.hout; g.stride = c.stride; g.pad = c.pad; g.kw = c.k; g.cblocks = c.cin / 32;
+    }
+    GPI_CUDA(gp::launch_vit_gemm(c.a_hi, c.a_lo, c.w_hi, c.w_lo, g, h->num_sms, s));
+    ++launched;
+  }
+  if (dump) {
+    const Conv& c = h->convs[last - 1];
+    if (c.out_buf < 0) return gp_internal_fail(GP_ERR_INVALID, "the last convolution writes `feat` directly; nothing to dump");
+    const long long cnt = (long long)n * c.hout * c.hout * c.cout;
+    merge_planes_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(h->act[c.out_buf].hi), reinterpret_cast<const __nv_bfloat16*>(h->act[c.out_buf].lo),
+        cnt, dump);
+    GPI_CUDA(cudaGetLastError());
+    ++launched;
+  }
+  gp_internal_count_launches(launched);
+  return GP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gp_ist_trunk_query_sizes(int max_crops, size_t* weight_bytes, size_t* workspace_bytes) {
+  if (max_crops < 1) return gp_internal_fail(GP_ERR_INVALID, "bad max_crops");
+  Carver cw(nullptr), cs(nullptr);
+  carve_weights(cw, nullptr, make_schedule());
+  carve_workspace(cs, max_crops, nullptr);
+  if (weight_bytes) *weight_bytes = cw.off;
+  if (workspace_bytes) *workspace_bytes = cs.off;
+  return GP_OK;
+}
+
+int gp_ist_trunk_create(int device, int max_crops, int precision, const gp_conv_weights_t* w, void* weight_mem,
+                        void* workspace_mem, void* stream, gp_ist_trunk_handle_t* out) {
+  if (max_crops < 1 || !w || !weight_mem || !workspace_mem || !out) return gp_internal_fail(GP_ERR_INVALID, "bad argument");
+  if (precision != GP_PRECISION_FP32_SPLIT && precision != GP_PRECISION_BF16)
+    return gp_internal_fail(GP_ERR_INVALID, "unknown precision %d", precision);
+  if (((uintptr_t)weight_mem | (uintptr_t)workspace_mem) & (kAlign - 1))
+    return gp_internal_fail(GP_ERR_INVALID, "weight and workspace memory must be 1024-byte aligned");
+  for (int i = 0; i < kNumConvs; ++i)
+    if (!w[i].weight) return gp_internal_fail(GP_ERR_INVALID, "weight pointer %d is null", i);
+  GPI_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GPI_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return gp_internal_fail(GP_ERR_UNSUPPORTED, "device %d is not sm_100", device);
+  gp_ist_trunk_context* h = new (std::nothrow) gp_ist_trunk_context();
+  if (!h) return gp_internal_fail(GP_ERR_INVALID, "out of host memory");
+  h->max_crops = max_crops; h->num_sms = prop.multiProcessorCount;
+  h->passes = precision == GP_PRECISION_FP32_SPLIT ? 3 : 1;
+  h->convs = make_schedule();
+  Carver cw(weight_mem), cs(workspace_mem);
+  carve_weights(cw, h, h->convs);
+  carve_workspace(cs, max_crops, h);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t ce = cudaMemsetAsync(const_cast<float*>(h->zero_bias), 0, 512 * sizeof(float), s);
+  int e = GP_OK;
+  for (int i = 0; i < kNumConvs && !e && ce == cudaSuccess; ++i) {
+    Conv& c = h->convs[i];
+    c.bias = w[i].bias;
+    // weights arrive as [cout, ky, kx, cin] (BatchNorm folded): exactly the [N, K] operand with K = (tap, channel)
+    ce = gp::launch_split_planes(w[i].weight, c.cout, c.K, c.Kpad, c.w.hi, c.w.lo, s);
+    if (ce != cudaSuccess) break;
+    if ((e = gp_internal_make_map(&c.w_hi, c.w.hi, c.cout, c.Kpad, c.bn)) || (e = gp_internal_make_map(&c.w_lo, c.w.lo, c.cout, c.Kpad, c.bn)))
+      break;
+    if (c.in_buf < 0) {                                   // stem: plain GEMM over the im2col planes
+      const uint64_t rows = (uint64_t)max_crops * kStemOut * kStemOut;
+      (e = gp_internal_make_map(&c.a_hi, h->stem.hi, rows, kStemKPad, 128)) || (e = gp_internal_make_map(&c.a_lo, h->stem.lo, rows, kStemKPad, 128));
+    } else if (c.k == 1 && c.stride == 1) {               // 1x1/1: the NHWC plane is already the [pixels, cin] operand
+      const uint64_t rows = (uint64_t)max_crops * c.hin * c.hin;
+      (e = gp_internal_make_map(&c.a_hi, h->act[c.in_buf].hi, rows, c.cin, 128)) ||
+          (e = gp_internal_make_map(&c.a_lo, h->act[c.in_buf].lo, rows, c.cin, 128));
+    } else {
+      const uint32_t ow = c.hout, oh = 128 / c.hout;
+      (e = gp_internal_make_map_nhwc(&c.a_hi, h->act[c.in_buf].hi, c.cin, c.hin, c.hin, max_crops, ow, oh, c.stride)) ||
+          (e = gp_internal_make_map_nhwc(&c.a_lo, h->act[c.in_buf].lo, c.cin, c.hin, c.hin, max_crops, ow, oh, c.stride));
+    }
+  }
+  if (ce != cudaSuccess) { delete h; return gp_internal_fail(GP_ERR_CUDA, "weight packing failed: %s", cudaGetErrorString(ce)); }
+  if (e) { delete h; return e; }
+  gp_internal_count_launches(kNumConvs);
+  *out = h;
+  return GP_OK;
+}
+
+int gp_ist_trunk_destroy(gp_ist_trunk_handle_t h) {
+  delete h;
+  return GP_OK;
+}
+
+int gp_ist_trunk_forward(gp_ist_trunk_handle_t h, int n, const float* crops, float* feat, void* stream) {
+  if (!h || !crops || !feat) return gp_internal_fail(GP_ERR_INVALID, "null argument");
+  if (n < 1 || n > h->max_crops) return gp_internal_fail(GP_ERR_INVALID, "batch %d outside [1, %d]", n, h->max_crops);
+  return run(h, n, crops, feat, 0, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int gp_debug_ist_trunk(gp_ist_trunk_handle_t h, int n, const float* crops, int num_convs, float* activation, void* stream) {
+  if (!h || !crops || !activation) return gp_internal_fail(GP_ERR_INVALID, "null argument");
+  if (n < 1 || n > h->max_crops) return gp_internal_fail(GP_ERR_INVALID, "batch %d outside [1, %d]", n, h->max_crops);
+  if (num_convs < 1 || num_convs >= kNumConvs) return gp_internal_fail(GP_ERR_INVALID, "num_convs outside [1, %d)", kNumConvs);
+  return run(h, n, crops, nullptr, num_convs, activation, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -26,7 +26,6 @@ constexpr int kWPlane = kBN * kRowBytes;          // 16 KB
 constexpr int kStageBytes = 2 * kAPlane + 2 * kWPlane;   // 48 KB
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 4 * 32 + kEpiWarps * 32;
-constexpr uint32_t kIdesc = umma_idesc_f16(kBM, kBN, 1);
 
 struct __align__(8) GemmSmemTail {
   float bias_s[2][kBN];                           // per-tile bias / LayerScale columns, double buffered with the accumulator
@@ -74,7 +73,9 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   GemmSmemTail& tail = *reinterpret_cast<GemmSmemTail*>(smem + kStages * kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int passes = p.passes;
-  const int num_m = (p.M + kBM - 1) / kBM, num_n = p.N / kBN;
+  const int bn = p.bn > 0 ? p.bn : kBN;                     // 128 / 192 / 256 output columns per tile
+  const uint32_t idesc = umma_idesc_f16(kBM, bn, 1);
+  const int num_m = (p.M + kBM - 1) / kBM, num_n = p.N / bn;
   const int num_tiles = num_m * num_n;
   const int num_kb = p.K / kBlockK;
 
@@ -97,21 +98,29 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx = (passes == 3 ? 2 : 1) * (kAPlane + kWPlane);
+      const uint32_t tx = (passes == 3 ? 2 : 1) * (kAPlane + bn * kRowBytes);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int mt, nt;
         tile_coords(tile, num_m, num_n, mt, nt);
-        const int m0 = mt * kBM, n0 = nt * kBN;
+        const int m0 = mt * kBM, n0 = nt * bn;
+        int img = 0, y0 = 0;
+        if (p.conv) { const int hw = p.Ho * p.Wo; img = m0 / hw; y0 = (m0 - img * hw) / p.Wo; }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&tail.empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * kStageBytes;
           mbar_arrive_expect_tx(&tail.full_bar[stage], tx);
-          tma_load_2d(st, &tm_a_hi, &tail.full_bar[stage], kb * kBlockK, m0);
-          tma_load_2d(st + 2 * kAPlane, &tm_w_hi, &tail.full_bar[stage], kb * kBlockK, n0);
-          if (passes == 3) {
-            tma_load_2d(st + 2 * kAPlane + kWPlane, &tm_w_lo, &tail.full_bar[stage], kb * kBlockK, n0);
-            tma_load_2d(st + kAPlane, &tm_a_lo, &tail.full_bar[stage], kb * kBlockK, m0);
+          if (p.conv) {           // k-block = (tap ky,kx ; 32-channel block cb): a shifted, strided window of the NHWC plane
+            const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+            const int ky = tap / p.kw, kx = tap - ky * p.kw;
+            const int cx = kx - p.pad, cy = y0 * p.stride + ky - p.pad;
+            tma_load_4d(st, &tm_a_hi, &tail.full_bar[stage], cb * kBlockK, cx, cy, img);
+            if (passes == 3) tma_load_4d(st + kAPlane, &tm_a_lo, &tail.full_bar[stage], cb * kBlockK, cx, cy, img);
+          } else {
+            tma_load_2d(st, &tm_a_hi, &tail.full_bar[stage], kb * kBlockK, m0);
+            if (passes == 3) tma_load_2d(st + kAPlane, &tm_a_lo, &tail.full_bar[stage], kb * kBlockK, m0);
           }
+          tma_load_2d(st + 2 * kAPlane, &tm_w_hi, &tail.full_bar[stage], kb * kBlockK, n0);
+          if (passes == 3) tma_load_2d(st + 2 * kAPlane + kWPlane, &tm_w_lo, &tail.full_bar[stage], kb * kBlockK, n0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -136,7 +145,7 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
               const uint32_t a = (pass == 2 ? a_lo : a_hi), w = (pass == 1 ? w_lo : w_hi);
 #pragma unroll
               for (int k16 = 0; k16 < kBlockK / 16; ++k16)
-                umma_f16(d, umma_desc_kmajor<kRowBytes>(a + k16 * 32), umma_desc_kmajor<kRowBytes>(w + k16 * 32), kIdesc,
+                umma_f16(d, umma_desc_kmajor<kRowBytes>(a + k16 * 32), umma_desc_kmajor<kRowBytes>(w + k16 * 32), idesc,
                          (kb | pass | k16) != 0 ? 1u : 0u);
             }
           }
@@ -157,15 +166,18 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       int mt, nt;
       tile_coords(tile, num_m, num_n, mt, nt);
       const int m = mt * kBM + r;
-      const int ntile0 = nt * kBN;
-      const int n0 = ntile0 + ch * 128;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + ch * 128;
+      const int ntile0 = nt * bn;
+      const int half_cols = bn >> 1;                   // columns per epilogue warp: 64 / 96 / 128
+      const int n0 = ntile0 + ch * half_cols;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + ch * half_cols;
       // stage the per-column vectors of this tile (256 epilogue threads, one column each)
-      tail.bias_s[acc][etid] = __ldg(p.bias + ntile0 + etid);
-      if (p.mode == GEMM_SCALE_RESIDUAL) tail.gamma_s[acc][etid] = __ldg(p.gamma + ntile0 + etid);
+      if (etid < bn) {
+        tail.bias_s[acc][etid] = __ldg(p.bias + ntile0 + etid);
+        if (p.mode == GEMM_SCALE_RESIDUAL) tail.gamma_s[acc][etid] = __ldg(p.gamma + ntile0 + etid);
+      }
       named_barrier_sync(1, kEpiWarps * 32);
-      const float* sb = tail.bias_s[acc] + ch * 128;
-      const float* sg = tail.gamma_s[acc] + ch * 128;
+      const float* sb = tail.bias_s[acc] + ch * half_cols;
+      const float* sg = tail.gamma_s[acc] + ch * half_cols;
       const bool row_ok = m < p.M;
       size_t out_row = (size_t)m;
       const float* pos_row = nullptr;
@@ -222,12 +234,24 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(v32[j]) + sb[c0 + j];
-        if (p.mode == GEMM_PLANES || p.mode == GEMM_PLANES_GELU || p.mode == GEMM_QKV_HEADS) {
+        if (p.mode == GEMM_PLANES || p.mode == GEMM_PLANES_GELU || p.mode == GEMM_QKV_HEADS || p.mode == GEMM_PLANES_RELU ||
+            p.mode == GEMM_PLANES_ADD_RELU) {
           uint32_t hi[16], lo[16];
+          if (p.mode == GEMM_PLANES_ADD_RELU) {          // BasicBlock: relu(shortcut + bn2(conv2(.)))   (resnet.py:45-50)
+            const size_t rb = (out_row * p.N + n) * 2;
+            load_rows_64B(hi, reinterpret_cast<const uint8_t*>(p.res_hi), rb);
+            load_rows_64B(lo, reinterpret_cast<const uint8_t*>(p.res_lo), rb);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              v[2 * j] += __uint_as_float(hi[j] << 16) + __uint_as_float(lo[j] << 16);
+              v[2 * j + 1] += __uint_as_float(hi[j] & 0xffff0000u) + __uint_as_float(lo[j] & 0xffff0000u);
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             float a = v[j], b = v[j + 1];
             if (p.mode == GEMM_PLANES_GELU) { a = gelu_erf(a); b = gelu_erf(b); }
+            if (p.mode == GEMM_PLANES_RELU || p.mode == GEMM_PLANES_ADD_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
             const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
             hi[j >> 1] = pack_bf16(ah, bh);
             lo[j >> 1] = pack_bf16(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
@@ -251,6 +275,15 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
               w[j] = __float_as_uint(__uint_as_float(w[j]) + sg[c0 + half * 16 + j] * v[half * 16 + j]);
             store_rows_64B(w, reinterpret_cast<uint8_t*>(p.x), rowb + half * 64);
           }
+        } else if (p.mode == GEMM_ROWS_F32) {             // plain fp32 rows (final 1x1 convolution of the IST trunk)
+          const size_t rowb = (out_row * p.N + n) * 4;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(v[half * 16 + j]);
+            store_rows_64B(w, reinterpret_cast<uint8_t*>(p.x), rowb + half * 64);
+          }
         } else {                                          // GEMM_PATCH_EMBED
           const size_t rowb = (out_row * p.N + n) * 4;
 #pragma unroll
@@ -264,24 +297,38 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         }
       };
 
-      // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is processed
+      // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is processed; the accumulator
+      // goes back to the UMMA warp as soon as its last chunk is in registers
+      const int nchunks = half_cols >> 5;               // 2, 3 or 4 chunks of 32 columns
       uint32_t va[32], vb[32];
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail.tmem_empty_bar[acc]);
+      };
       tmem_ld_32x32(taddr, va);
       tmem_ld_wait_for(va);
       tmem_ld_32x32(taddr + 32, vb);
       process(va, 0);
       tmem_ld_wait_for(vb);
-      tmem_ld_32x32(taddr + 64, va);
-      process(vb, 32);
-      tmem_ld_wait_for(va);
-      tmem_ld_32x32(taddr + 96, vb);
-      process(va, 64);
-      tmem_ld_wait_for(vb);
-      // accumulator fully read -> hand it back to the UMMA warp before the last chunk's math / stores
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tail.tmem_empty_bar[acc]);
-      process(vb, 96);
+      if (nchunks == 2) {
+        release_acc();
+        process(vb, 32);
+      } else {
+        tmem_ld_32x32(taddr + 64, va);
+        process(vb, 32);
+        tmem_ld_wait_for(va);
+        if (nchunks == 3) {
+          release_acc();
+          process(va, 64);
+        } else {
+          tmem_ld_32x32(taddr + 96, vb);
+          process(va, 64);
+          tmem_ld_wait_for(vb);
+          release_acc();
+          process(vb, 96);
+        }
+      }
       if (e == 0 && lane == 0) GSTAMP(unit * 4 + 3);
     }
   }
@@ -305,8 +352,10 @@ cudaError_t launch_vit_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, co
     configured = true;
   }
   if (p.M <= 0) return cudaSuccess;
-  if (p.N % kBN != 0 || p.K % kBlockK != 0) return cudaErrorInvalidValue;
-  const int tiles = ((p.M + kBM - 1) / kBM) * (p.N / kBN);
+  const int bn = p.bn > 0 ? p.bn : kBN;
+  if ((bn != 128 && bn != 192 && bn != 256) || p.N % bn != 0 || p.K % kBlockK != 0) return cudaErrorInvalidValue;
+  if (p.conv && (p.Wo <= 0 || 128 % p.Wo != 0 || p.M % kBM != 0 || p.cblocks <= 0)) return cudaErrorInvalidValue;
+  const int tiles = ((p.M + kBM - 1) / kBM) * (p.N / bn);
   const int grid = tiles < num_sms ? tiles : num_sms;
   vit_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(a_hi, a_lo, w_hi, w_lo, p);
   return cudaGetLastError();

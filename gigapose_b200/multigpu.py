@@ -175,7 +175,8 @@ def run_sharded_bench(args, cfg, config, wl_name, rank, world, device, METRIC, U
     """bench.py body for N > 1 (launched by torch.distributed.run, one rank per GPU)."""
     import bench
     from . import vit_engine
-    model = bench.build_models(device)
+    ist_backend = getattr(args, "ist_backend", "native")
+    model = bench.build_models(device, ist_backend=ist_backend)
     templates = bench.SyntheticTemplates(cfg["O"], cfg["T"], device)
     B = cfg["B"]
     retr = ShardedRetriever(model, templates, rank, world, device, max_batch=B)
@@ -241,12 +242,12 @@ def run_sharded_bench(args, cfg, config, wl_name, rank, world, device, METRIC, U
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "strong" if wl_name == "c2" else "weak", "vs_baseline": None,
                 "dtype": "f32 (a1, a4: bf16 hi/lo split x3 on tensor cores with fp32 accumulate = fp32-faithful; a5, a7-a9: fp32; "
-                         "a6: fp32 cuDNN)",
+                         + ("a6: same split on the implicit-GEMM convolutions)" if ist_backend == "native" else "a6: TF32 cuDNN)"),
                 "data": "synthetic",
                 "config": dict(config, parallelism=f"template-interleaved bank shards x{world}, crops data-parallel, "
                                                    "1 all-gather of features + 1 all-gather of top-k records per batch",
-                               native_rows=[f"a1 ViT-L/14 ({vit_engine.BACKEND})", "a2", "a3", "a4", "a5", "a7", "a8", "a9", "e"],
-                               library_rows=["a6 IST ResNet (cuDNN via torch, SURVEY f1 'next')"],
+                               **{kk: (vv + ["e"] if kk == "native_rows" else vv)
+                                  for kk, vv in bench.rows_config(ist_backend).items()},
                                planted_view_in_topk=hit),
                 "clocks": clocks.summary(),
                 "e2e": {"value": B / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,

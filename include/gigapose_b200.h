@@ -194,6 +194,28 @@ int gp_vit_destroy(gp_vit_handle_t h);
  * (DinoVisionTransformer.forward_features()["x_prenorm"], the tensor ae_net.py:65 slices). */
 int gp_vit_forward(gp_vit_handle_t h, int b, const float* img, float* x_prenorm, void* stream);
 
+/* --- rows a6 / f1: IST trunk (ResNet, resnet.py:318-381 called at ist_net.py:62-63), BatchNorm folded ------------ */
+#define GP_IST_TRUNK_NUM_CONVS 21
+typedef struct gp_ist_trunk_context* gp_ist_trunk_handle_t;
+/* One convolution with its inference-time BatchNorm folded in (w * gamma / sqrt(var + eps), beta - mean * gamma / ...):
+ *   weight f32 [cout, kh, kw, cin] (channels-last filter), bias f32 [cout] or NULL. */
+typedef struct {
+  const float* weight;
+  const float* bias;
+} gp_conv_weights_t;
+
+int gp_ist_trunk_query_sizes(int max_crops, size_t* weight_bytes, size_t* workspace_bytes);
+/* `convs`: GP_IST_TRUNK_NUM_CONVS entries in execution order -- conv1+bn1 (7x7/2, 3->128); for layer1..layer4 and block
+ * 0,1: conv1+bn1 (3x3), [block 0 of layer2..4: downsample.0+downsample.1 (1x1/2),] conv2+bn2 (3x3); layer4_outconv
+ * (1x1, 512->256, no bias).  Geometry is the shipped config (configs/model/ist_net/resnet.yaml: input 256, dims
+ * 128/192/256/512, descriptor 256).  Weights are packed into `weight_mem` on `stream`; biases are referenced in place. */
+int gp_ist_trunk_create(int device, int max_crops, int precision, const gp_conv_weights_t* convs, void* weight_mem,
+                        void* workspace_mem, void* stream, gp_ist_trunk_handle_t* out);
+int gp_ist_trunk_destroy(gp_ist_trunk_handle_t h);
+/* crops f32 [n,3,224,224] (normalised RGB) -> feat f32 [n,256 patches,256 channels]: the [n,256,16,16] map
+ * ISTNet.forward_by_chunk returns (ist_net.py:52-64), stored patch-major (the layout gp_bank_write / gp_ist_mlp keep). */
+int gp_ist_trunk_forward(gp_ist_trunk_handle_t h, int n, const float* crops, float* feat, void* stream);
+
 /* --- diagnostics ----------------------------------------------------------------------------------------- */
 /* number of kernels this library has launched since load (all handles); used for bench.py's `gpu_launches` */
 uint64_t gp_launch_count(void);
@@ -208,6 +230,8 @@ int gp_debug_attention_timeline(long long* stamps32);
 /* same for CTA 0 of the last QKV-shaped ViT GEMM: 64 int64: [4*tile + {0: UMMA start, 1: UMMA issued, 2: epilogue
  * start, 3: epilogue end}], [63] = kernel start. */
 int gp_debug_gemm_timeline(long long* stamps64);
+/* runs the first `num_convs` convolutions of the trunk and writes the last one's output as f32 NHWC */
+int gp_debug_ist_trunk(gp_ist_trunk_handle_t h, int n, const float* crops, int num_convs, float* activation, void* stream);
 
 /* test hook: runs the similarity kernel and additionally dumps the raw fp32 similarity tiles, laid out
  * [item = n * B + j][256 t][256 s] where j indexes the queries sorted by object id (B <= 32, small sizes only). */

@@ -1,9 +1,10 @@
 """`ResNet` -- the IST backbone (reference `src/models/network/resnet.py:26-50,318-381`; Hydra target
 `src.models.network.resnet.ResNet`, configs/model/ist_net/resnet.yaml:6).
 
-Row a6 / f1 of SURVEY.md §8: this stage is the one allowed to stay on library kernels (cuDNN convolutions through
-torch) until its native implicit-GEMM version lands; it is listed as `library` in bench.py.  Parameter names match
-the reference state dict (`conv1, bn1, layer{1..4}.{0,1}.{conv1,conv2,bn1,bn2,downsample.{0,1}}, layer4_outconv`).
+Rows a6 / f1 of SURVEY.md §8.  Inference on a CUDA device (`eval()`, no grad, 224x224 crops, shipped geometry) runs
+on the native tcgen05 implicit-GEMM kernels (`gigapose_b200/ist_trunk.py`, csrc/ist_trunk.cu); `backend = "cudnn"`
+selects the BatchNorm-folded cuDNN path instead (TF32 convolutions; kept for comparison and for other geometries), and
+training / autograd uses the plain torch modules.  Parameter names match the reference state dict (`conv1, bn1, layer{1..4}.{0,1}.{conv1,conv2,bn1,bn2,downsample.{0,1}}, layer4_outconv`).
 The optional attention blocks of the reference (n_heads > 0) are dead under the shipped config and not provided.
 """
 import torch
@@ -42,6 +43,7 @@ class ResNet(nn.Module):
         if config.get("n_heads", 0) > 0:
             raise NotImplementedError("SpatialTransformer blocks (n_heads > 0) are not part of the shipped config")
         self.input_size = config["input_size"]
+        self.backend = config.get("backend", "native")        # "native" (tcgen05 kernels) | "cudnn"
         width = config["initial_dim"]
         dims = list(config["block_dims"])
         self.conv1 = nn.Conv2d(config["input_dim"], width, 7, stride=2, padding=3, bias=False)
@@ -58,8 +60,13 @@ class ResNet(nn.Module):
 
     def forward(self, x):
         # the reference resizes 224 -> 256 with align_corners=True before the trunk (resnet.py:365-368)
+        inference = not self.training and x.is_cuda and not torch.is_grad_enabled()
+        if inference and self.backend == "native" and tuple(x.shape[1:]) == (3, 224, 224):
+            from gigapose_b200 import ist_trunk
+            if ist_trunk.supports(self):
+                return ist_trunk.trunk_forward(self, x)      # resize, 21 convolutions, BN, ReLU, shortcuts: all native
         x = F.interpolate(x, (self.input_size, self.input_size), mode="bilinear", align_corners=True)
-        if not self.training and x.is_cuda and not torch.is_grad_enabled():
+        if inference:
             return self._forward_folded(x)
         x = F.relu(self.bn1(self.conv1(x)))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))

@@ -128,24 +128,27 @@ def test_gigapose_module_end_to_end_small():
     assert eng.launch_count() > 0
 
 
-def test_ist_backbone_matches_oracle(golden_dir):
-    """Row a6 (library stage: cuDNN through torch, BN folded, NHWC).  cuDNN convolutions run in TF32 by torch's default
-    (the reference's own GPU behaviour), hence the 3e-3 relative tolerance against the fp32 CPU oracle."""
+@pytest.mark.parametrize("backend,tol", [("native", 3e-4), ("cudnn", 3e-3)])
+def test_ist_backbone_matches_oracle(golden_dir, backend, tol):
+    """Row a6 against the fp32 CPU oracle's golden features.  native: tcgen05 implicit-GEMM trunk with fp32-faithful
+    split products (observed 7e-5 of the feature range after 21 layers).  cudnn: the BN-folded library path, whose
+    convolutions run in TF32 by torch's default (the reference's own GPU behaviour), hence 3e-3."""
     import os
     import numpy as np
     from src.models.network.resnet import ResNet
     ref = port.ISTBackbonePort()
     net = ResNet(dict(n_heads=0, input_dim=3, input_size=256, initial_dim=128, block_dims=[128, 192, 256, 512],
-                      descriptor_size=256))
+                      descriptor_size=256, backend=backend))
     net.load_state_dict(ref.state_dict())
     net = net.to(DEV).eval()
     rgb, _ = synth.make_crops(2, seed=31)
     with torch.no_grad():
         got = net(rgb.to(DEV)).cpu()
+    assert (getattr(net, "_gp_trunk_engine", None) is not None) == (backend == "native")
     g = np.load(os.path.join(golden_dir, "backbones.npz"))
     want = torch.from_numpy(g["ist_feat_sub"])
     scale = want.abs().max().item()
-    assert (got[:, ::2] - want).abs().max().item() < 3e-3 * scale
+    assert (got[:, ::2] - want).abs().max().item() < tol * scale
 
 
 def test_test_step_writes_reference_npz_schema(tmp_path):
