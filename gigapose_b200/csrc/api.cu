@@ -13,6 +13,8 @@
 
 int gp_internal_make_map_nhwc(CUtensorMap* map, void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint32_t out_w,
                               uint32_t out_h, uint32_t stride);
+int gp_internal_make_map_raw(CUtensorMap* map, void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                             const uint32_t* box, const uint32_t* elem_strides);
 int gp_internal_make_map_ex(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows,
                             int swizzle_bytes);
 
@@ -111,6 +113,20 @@ int gp_internal_make_map_nhwc(CUtensorMap* map, void* ptr, uint64_t C, uint64_t 
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(GP_ERR_CUDA, "cuTensorMapEncodeTiled (NHWC) failed with CUresult %d", (int)r);
+  return GP_OK;
+}
+// bf16 tensor map with caller-chosen dimensions / byte strides (rank <= 5, SWIZZLE_64B): used for views whose rows
+// overlap in memory (the stem's sliding 8-pixel windows, ist_trunk.cu)
+int gp_internal_make_map_raw(CUtensorMap* map, void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                             const uint32_t* box, const uint32_t* elem_strides) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(GP_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from this driver");
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = elem_strides[i]; if (i + 1 < rank) st[i] = strides_bytes[i]; }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, ptr, d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GP_ERR_CUDA, "cuTensorMapEncodeTiled (raw, rank %d) failed with CUresult %d", rank, (int)r);
   return GP_OK;
 }
 // [rows, cols] plane, box = 32 columns (SWIZZLE_64B) x box_rows

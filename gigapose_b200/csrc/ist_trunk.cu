@@ -7,7 +7,10 @@
 // NHWC bf16 hi/lo planes, one output tile = 128 consecutive output pixels (whole output rows of one image) x all / half
 // of the output channels, and the A operand of k-block (ky, kx, 32-channel block) is fetched by ONE 4-D TMA box per
 // plane -- a shifted, strided window of the input plane whose out-of-image part TMA zero-fills (the padding).  No
-// im2col buffer exists except for the 3-channel stem (K = 7*7*3 = 147 -> 160 columns), which also fuses the resize.
+// im2col buffer exists anywhere.  The 3-channel stem reads the resized crop, stored as zero-bordered NHWC planes with 4
+// channels, through a tensor map whose rows OVERLAP: row xo of the view is the 8-pixel x 4-channel window starting at
+// pixel 2*xo - 4 (16-byte row pitch, 64-byte rows), so that one k-block is one filter row ky (K = 7 x 32 = 224 with
+// zero filter entries for the 8th pixel and the 4th channel).
 // ReLU, the residual add and the hi/lo split of the next layer's input are the GEMM epilogue.
 #include "../../include/gigapose_b200.h"
 #include "gigapose_kernels.h"
@@ -19,12 +22,15 @@
 extern int gp_internal_fail(int code, const char* fmt, ...);
 extern void gp_internal_count_launches(int n);
 extern int gp_internal_make_map(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
+extern int gp_internal_make_map_raw(CUtensorMap* map, void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                                    const uint32_t* box, const uint32_t* elem_strides);
 extern int gp_internal_make_map_nhwc(CUtensorMap* map, void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t N,
                                      uint32_t out_w, uint32_t out_h, uint32_t stride);
 
 namespace {
 
-constexpr int kIn = 224, kRes = 256, kStemOut = 128, kStemK = 147, kStemKPad = 160, kFeat = 256;
+constexpr int kIn = 224, kRes = 256, kStemOut = 128, kStemKPad = 224, kFeat = 256;
+constexpr int kPadRows = kRes + 6, kPadCols = kRes + 8;     // resized crop with 3 zero rows above / below, 4 zero pixels left / right
 constexpr int kDims[4] = {128, 192, 256, 512};
 constexpr int kNumConvs = GP_IST_TRUNK_NUM_CONVS;
 constexpr size_t kAlign = 1024;
@@ -41,6 +47,7 @@ struct Planes { uint16_t *hi = nullptr, *lo = nullptr; };
 struct Conv {
   int cin, cout, k, stride, pad, hin, hout;     // square maps and filters
   int K, Kpad, bn, mode;
+  int swap;                                     // 128-channel layers: filters are the 128-row UMMA operand (vit_gemm.cu)
   int in_buf, out_buf, res_buf;                 // activation buffers (-1: stem im2col planes / none)
   Planes w;
   const float* bias;
@@ -53,8 +60,9 @@ std::vector<Conv> make_schedule() {
   auto add = [&](int cin, int cout, int k, int stride, int pad, int hin, int mode, int in_buf, int out_buf, int res_buf) {
     Conv c{};
     c.cin = cin; c.cout = cout; c.k = k; c.stride = stride; c.pad = pad; c.hin = hin; c.hout = hin / stride;
-    c.K = k * k * cin; c.Kpad = (c.K + 31) / 32 * 32;
-    c.bn = cout == 128 ? 128 : (cout == 192 ? 192 : 256);
+    c.K = k * k * cin; c.Kpad = cin == 3 ? kStemKPad : c.K;
+    c.swap = cout == 128 ? 1 : 0;
+    c.bn = cout == 192 ? 192 : 256;
     c.mode = mode; c.in_buf = in_buf; c.out_buf = out_buf; c.res_buf = res_buf;
     v.push_back(c);
   };
@@ -91,33 +99,39 @@ __device__ __forceinline__ void split_store(float v, __nv_bfloat16* hi, __nv_bfl
   lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
-// Bilinear 224 -> 256 (align_corners=True, resnet.py:365-368) fused with the stem's im2col:
-// planes[(img*128 + yo)*128 + xo][(ky*7 + kx)*3 + c] = resized[img][c][2*yo + ky - 3][2*xo + kx - 3]  (0 outside).
-__global__ void stem_im2col_kernel(const float* __restrict__ img, int n, __nv_bfloat16* __restrict__ hi,
-                                   __nv_bfloat16* __restrict__ lo) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)n * kStemOut * kStemOut * kStemKPad;
-  if (i >= total) return;
-  const long long row = i / kStemKPad;
-  const int k = (int)(i - row * kStemKPad);
-  float v = 0.f;
-  if (k < kStemK) {
-    const int im = (int)(row / (kStemOut * kStemOut)), pix = (int)(row - (long long)im * kStemOut * kStemOut);
-    const int yo = pix / kStemOut, xo = pix - yo * kStemOut;
-    const int tap = k / 3, c = k - tap * 3, ky = tap / 7, kx = tap - ky * 7;
-    const int y = 2 * yo + ky - 3, x = 2 * xo + kx - 3;
-    if (y >= 0 && y < kRes && x >= 0 && x < kRes) {
-      const float scale = (float)(kIn - 1) / (float)(kRes - 1);
-      const float fy = scale * y, fx = scale * x;
-      const int y0 = (int)fy, x0 = (int)fx;
-      const int yp = y0 < kIn - 1 ? 1 : 0, xp = x0 < kIn - 1 ? 1 : 0;
-      const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
-      const float* src = img + ((size_t)im * 3 + c) * kIn * kIn;
-      v = hy * (hx * src[y0 * kIn + x0] + lx * src[y0 * kIn + x0 + xp]) +
-          ly * (hx * src[(y0 + yp) * kIn + x0] + lx * src[(y0 + yp) * kIn + x0 + xp]);
-    }
+// Bilinear 224 -> 256 (align_corners=True, resnet.py:365-368) into zero-bordered NHWC4 hi/lo planes
+// [img][262 rows][264 pixels][4]: pixel (y, x) of the resized crop lives at row y + 3, column x + 4.
+__global__ void resize_pad_kernel(const float* __restrict__ img, int n, uint2* __restrict__ hi, uint2* __restrict__ lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * kRes * kRes) return;
+  const int im = i / (kRes * kRes), pix = i - im * kRes * kRes, y = pix / kRes, x = pix - y * kRes;
+  const float scale = (float)(kIn - 1) / (float)(kRes - 1);
+  const float fy = scale * y, fx = scale * x;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int yp = y0 < kIn - 1 ? 1 : 0, xp = x0 < kIn - 1 ? 1 : 0;
+  const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+  uint32_t h[3], l[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* src = img + ((size_t)im * 3 + c) * kIn * kIn;
+    const float v = hy * (hx * src[y0 * kIn + x0] + lx * src[y0 * kIn + x0 + xp]) +
+                    ly * (hx * src[(y0 + yp) * kIn + x0] + lx * src[(y0 + yp) * kIn + x0 + xp]);
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    h[c] = __bfloat16_as_ushort(b);
+    l[c] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(b)));
   }
-  split_store(v, hi, lo, (size_t)i);
+  const size_t o = ((size_t)im * kPadRows + y + 3) * kPadCols + x + 4;
+  hi[o] = make_uint2(h[0] | (h[1] << 16), h[2]);
+  lo[o] = make_uint2(l[0] | (l[1] << 16), l[2]);
+}
+
+// Stem filter [128, 7, 7, 3] (cout, ky, kx, c) -> [128, 7, 8, 4] = [128, 224] hi/lo planes: window pixel i holds tap
+// kx = i - 1 (pixel 0 of a window lies left of the 7 taps), channel 3 does not exist; both get zero weights.
+__global__ void pack_stem_filter_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kStemOut * kStemKPad) return;
+  const int co = i / kStemKPad, k = i - co * kStemKPad, ky = k >> 5, px = (k >> 2) & 7, c = k & 3;
+  split_store(px >= 1 && c < 3 ? w[((co * 7 + ky) * 7 + (px - 1)) * 3 + c] : 0.f, hi, lo, (size_t)i);
 }
 
 __global__ void merge_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, long long n,
@@ -132,7 +146,7 @@ struct gp_ist_trunk_context {
   int max_crops, passes, num_sms;
   std::vector<Conv> convs;
   Planes act[4];               // NHWC activation planes, each sized for the largest map [max_crops,128,128,128]
-  Planes stem;                 // [max_crops*128*128, 160] im2col planes of the resized crop
+  Planes stem;                 // [max_crops, 262, 264, 4] zero-bordered resized crops (NHWC4)
   const float* zero_bias;      // [512] zeros (the output convolution has no bias)
 };
 
@@ -154,15 +168,14 @@ void carve_workspace(Carver& c, int max_crops, gp_ist_trunk_context* h) {
     uint16_t* a = c.take<uint16_t>(act); uint16_t* l = c.take<uint16_t>(act);
     if (h) { h->act[b].hi = a; h->act[b].lo = l; }
   }
-  const size_t st = (size_t)max_crops * kStemOut * kStemOut * kStemKPad;
+  const size_t st = (size_t)max_crops * kPadRows * kPadCols * 4;
   uint16_t* a = c.take<uint16_t>(st); uint16_t* l = c.take<uint16_t>(st);
   if (h) { h->stem.hi = a; h->stem.lo = l; }
 }
 
 int run(gp_ist_trunk_context* h, int n, const float* crops, float* feat, int stop_after, float* dump, cudaStream_t s) {
-  const long long stem_total = (long long)n * kStemOut * kStemOut * kStemKPad;
-  stem_im2col_kernel<<<(unsigned)((stem_total + 255) / 256), 256, 0, s>>>(
-      crops, n, reinterpret_cast<__nv_bfloat16*>(h->stem.hi), reinterpret_cast<__nv_bfloat16*>(h->stem.lo));
+  resize_pad_kernel<<<(n * kRes * kRes + 255) / 256, 256, 0, s>>>(crops, n, reinterpret_cast<uint2*>(h->stem.hi),
+                                                                  reinterpret_cast<uint2*>(h->stem.lo));
   GPI_CUDA(cudaGetLastError());
   int launched = 1;
   const int last = stop_after > 0 && stop_after < (int)h->convs.size() ? stop_after : (int)h->convs.size();
@@ -171,14 +184,18 @@ int run(gp_ist_trunk_context* h, int n, const float* crops, float* feat, int sto
     gp::GemmParams g{};
     g.passes = h->passes; g.mode = c.mode; g.bn = c.bn;
     g.M = n * c.hout * c.hout; g.N = c.cout; g.K = c.Kpad;
+    if (c.swap) { g.swap = 1; g.M = c.cout; g.N = n * c.hout * c.hout; }
     g.bias = c.bias ? c.bias : h->zero_bias;
     if (c.out_buf >= 0) { g.out_hi = h->act[c.out_buf].hi; g.out_lo = h->act[c.out_buf].lo; }
     else g.x = feat;
     if (c.res_buf >= 0) { g.res_hi = h->act[c.res_buf].hi; g.res_lo = h->act[c.res_buf].lo; }
-    if (c.in_buf >= 0 && !(c.k == 1 && c.stride == 1)) {
+    if (c.in_buf < 0) {          // stem: k-block = filter row ky over the overlapping-window view (x handled by the view)
+      g.conv = 1; g.Ho = c.hout; g.Wo = c.hout; g.stride = 2; g.pad = 0; g.kw = 1; g.cblocks = 1;
+    } else if (!(c.k == 1 && c.stride == 1)) {
       g.conv = 1; g.Ho = c.hout; g.Wo = c.hout; g.stride = c.stride; g.pad = c.pad; g.kw = c.k; g.cblocks = c.cin / 32;
     }
-    GPI_CUDA(gp::launch_vit_gemm(c.a_hi, c.a_lo, c.w_hi, c.w_lo, g, h->num_sms, s));
+    if (c.swap) GPI_CUDA(gp::launch_vit_gemm(c.w_hi, c.w_lo, c.a_hi, c.a_lo, g, h->num_sms, s));   // filters take the 128-row slot
+    else GPI_CUDA(gp::launch_vit_gemm(c.a_hi, c.a_lo, c.w_hi, c.w_lo, g, h->num_sms, s));
     ++launched;
   }
   if (dump) {
@@ -232,24 +249,40 @@ int gp_ist_trunk_create(int device, int max_crops, int precision, const gp_conv_
   carve_workspace(cs, max_crops, h);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t ce = cudaMemsetAsync(const_cast<float*>(h->zero_bias), 0, 512 * sizeof(float), s);
+  // the zero border (and 4th channel) of the resized-crop planes is written once; resize_pad_kernel fills the interior
+  const size_t stem_bytes = (size_t)max_crops * kPadRows * kPadCols * 4 * sizeof(uint16_t);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(h->stem.hi, 0, stem_bytes, s);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(h->stem.lo, 0, stem_bytes, s);
   int e = GP_OK;
   for (int i = 0; i < kNumConvs && !e && ce == cudaSuccess; ++i) {
     Conv& c = h->convs[i];
     c.bias = w[i].bias;
     // weights arrive as [cout, ky, kx, cin] (BatchNorm folded): exactly the [N, K] operand with K = (tap, channel)
-    ce = gp::launch_split_planes(w[i].weight, c.cout, c.K, c.Kpad, c.w.hi, c.w.lo, s);
+    if (c.in_buf < 0) {
+      pack_stem_filter_kernel<<<(kStemOut * kStemKPad + 255) / 256, 256, 0, s>>>(
+          w[i].weight, reinterpret_cast<__nv_bfloat16*>(c.w.hi), reinterpret_cast<__nv_bfloat16*>(c.w.lo));
+      ce = cudaGetLastError();
+    } else {
+      ce = gp::launch_split_planes(w[i].weight, c.cout, c.K, c.Kpad, c.w.hi, c.w.lo, s);
+    }
     if (ce != cudaSuccess) break;
-    if ((e = gp_internal_make_map(&c.w_hi, c.w.hi, c.cout, c.Kpad, c.bn)) || (e = gp_internal_make_map(&c.w_lo, c.w.lo, c.cout, c.Kpad, c.bn)))
+    const uint32_t wbox = c.swap ? 128 : c.bn, pix_tile = c.swap ? 256 : 128;    // rows per TMA box: filters / pixels
+    if ((e = gp_internal_make_map(&c.w_hi, c.w.hi, c.cout, c.Kpad, wbox)) || (e = gp_internal_make_map(&c.w_lo, c.w.lo, c.cout, c.Kpad, wbox)))
       break;
-    if (c.in_buf < 0) {                                   // stem: plain GEMM over the im2col planes
-      const uint64_t rows = (uint64_t)max_crops * kStemOut * kStemOut;
-      (e = gp_internal_make_map(&c.a_hi, h->stem.hi, rows, kStemKPad, 128)) || (e = gp_internal_make_map(&c.a_lo, h->stem.lo, rows, kStemKPad, 128));
+    if (c.in_buf < 0) {
+      // stem: {32 elements = 8 pixels x 4 channels, 128 windows at a 16-byte pitch, 262 rows, crops}; a 256-pixel tile
+      // is two output rows = every second input row starting at 2*yo + ky
+      const uint64_t dims[4] = {32, (uint64_t)kStemOut, (uint64_t)kPadRows, (uint64_t)max_crops};
+      const uint64_t strides[3] = {16, (uint64_t)kPadCols * 8, (uint64_t)kPadRows * kPadCols * 8};
+      const uint32_t box[4] = {32, (uint32_t)kStemOut, (pix_tile / kStemOut) * 2, 1}, es[4] = {1, 1, 2, 1};
+      (e = gp_internal_make_map_raw(&c.a_hi, h->stem.hi, 4, dims, strides, box, es)) ||
+          (e = gp_internal_make_map_raw(&c.a_lo, h->stem.lo, 4, dims, strides, box, es));
     } else if (c.k == 1 && c.stride == 1) {               // 1x1/1: the NHWC plane is already the [pixels, cin] operand
       const uint64_t rows = (uint64_t)max_crops * c.hin * c.hin;
-      (e = gp_internal_make_map(&c.a_hi, h->act[c.in_buf].hi, rows, c.cin, 128)) ||
-          (e = gp_internal_make_map(&c.a_lo, h->act[c.in_buf].lo, rows, c.cin, 128));
+      (e = gp_internal_make_map(&c.a_hi, h->act[c.in_buf].hi, rows, c.cin, pix_tile)) ||
+          (e = gp_internal_make_map(&c.a_lo, h->act[c.in_buf].lo, rows, c.cin, pix_tile));
     } else {
-      const uint32_t ow = c.hout, oh = 128 / c.hout;
+      const uint32_t ow = c.hout, oh = pix_tile / c.hout;
       (e = gp_internal_make_map_nhwc(&c.a_hi, h->act[c.in_buf].hi, c.cin, c.hin, c.hin, max_crops, ow, oh, c.stride)) ||
           (e = gp_internal_make_map_nhwc(&c.a_lo, h->act[c.in_buf].lo, c.cin, c.hin, c.hin, max_crops, ow, oh, c.stride));
     }

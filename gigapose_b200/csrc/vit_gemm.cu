@@ -65,6 +65,12 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
 __device__ long long g_gemm_stamp[64];
 #define GSTAMP(i) do { if (blockIdx.x == 0 && p.N == 3072 && (i) < 64) g_gemm_stamp[i] = clock64(); } while (0)
 
+// kSwap = false: rows of C are activation rows (tokens / output pixels), columns are output features.
+// kSwap = true (convolutions with 128 output channels): the roles are exchanged -- the 128-row UMMA operand is the
+// filter bank [128, K] and the 256-row operand is a tile of 256 output pixels, so that the tensor pipe still runs
+// M=128 x N=256 instructions (an N=128 instruction re-reads its operands from shared memory twice as often per FLOP
+// and is limited by shared-memory bandwidth); the epilogue transposes the [channel, pixel] accumulator back to NHWC.
+template <bool kSwap>
 __global__ void __launch_bounds__(kThreads, 1)
 vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, GemmParams p) {
@@ -104,23 +110,34 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         tile_coords(tile, num_m, num_n, mt, nt);
         const int m0 = mt * kBM, n0 = nt * bn;
         int img = 0, y0 = 0;
-        if (p.conv) { const int hw = p.Ho * p.Wo; img = m0 / hw; y0 = (m0 - img * hw) / p.Wo; }
+        if (p.conv) { const int hw = p.Ho * p.Wo, pix0 = kSwap ? n0 : m0; img = pix0 / hw; y0 = (pix0 - img * hw) / p.Wo; }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&tail.empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * kStageBytes;
           mbar_arrive_expect_tx(&tail.full_bar[stage], tx);
-          if (p.conv) {           // k-block = (tap ky,kx ; 32-channel block cb): a shifted, strided window of the NHWC plane
-            const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+          // the pixel operand (A, or W when kSwap) of a convolution: k-block = (tap ky,kx ; 32-channel block cb), a
+          // shifted, strided window of the NHWC plane; the other operand is a plain [rows, K] matrix
+          int cb = 0, cx = 0, cy = 0;
+          if (p.conv) {
+            const int tap = kb / p.cblocks;
+            cb = kb - tap * p.cblocks;
             const int ky = tap / p.kw, kx = tap - ky * p.kw;
-            const int cx = kx - p.pad, cy = y0 * p.stride + ky - p.pad;
+            cx = kx - p.pad; cy = y0 * p.stride + ky - p.pad;
+          }
+          if (p.conv && !kSwap) {
             tma_load_4d(st, &tm_a_hi, &tail.full_bar[stage], cb * kBlockK, cx, cy, img);
             if (passes == 3) tma_load_4d(st + kAPlane, &tm_a_lo, &tail.full_bar[stage], cb * kBlockK, cx, cy, img);
           } else {
             tma_load_2d(st, &tm_a_hi, &tail.full_bar[stage], kb * kBlockK, m0);
             if (passes == 3) tma_load_2d(st + kAPlane, &tm_a_lo, &tail.full_bar[stage], kb * kBlockK, m0);
           }
-          tma_load_2d(st + 2 * kAPlane, &tm_w_hi, &tail.full_bar[stage], kb * kBlockK, n0);
-          if (passes == 3) tma_load_2d(st + 2 * kAPlane + kWPlane, &tm_w_lo, &tail.full_bar[stage], kb * kBlockK, n0);
+          if (p.conv && kSwap) {
+            tma_load_4d(st + 2 * kAPlane, &tm_w_hi, &tail.full_bar[stage], cb * kBlockK, cx, cy, img);
+            if (passes == 3) tma_load_4d(st + 2 * kAPlane + kWPlane, &tm_w_lo, &tail.full_bar[stage], cb * kBlockK, cx, cy, img);
+          } else {
+            tma_load_2d(st + 2 * kAPlane, &tm_w_hi, &tail.full_bar[stage], kb * kBlockK, n0);
+            if (passes == 3) tma_load_2d(st + 2 * kAPlane + kWPlane, &tm_w_lo, &tail.full_bar[stage], kb * kBlockK, n0);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -171,7 +188,7 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       const int n0 = ntile0 + ch * half_cols;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + ch * half_cols;
       // stage the per-column vectors of this tile (256 epilogue threads, one column each)
-      if (etid < bn) {
+      if (!kSwap && etid < bn) {
         tail.bias_s[acc][etid] = __ldg(p.bias + ntile0 + etid);
         if (p.mode == GEMM_SCALE_RESIDUAL) tail.gamma_s[acc][etid] = __ldg(p.gamma + ntile0 + etid);
       }
@@ -229,7 +246,55 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         __syncwarp();
       };
 
+      // kSwap: thread = output channel m, the 32 columns of a chunk are 32 consecutive output pixels; every value is
+      // transposed through the warp's smem buffer so that a pixel's 32 channels leave as one 64-byte NHWC segment
+      auto process_swapped = [&](uint32_t (&v32)[32], int c0) {
+        const size_t pix = (size_t)(n0 + c0);
+        const size_t cbase = (size_t)(mt * kBM + q * 32);
+        const float bias_r = __ldg(p.bias + m);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(v32[j]) + bias_r;
+        auto rows_in = [&](const uint16_t* plane) {          // v[j] += plane[pix + j][channel of this lane]
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + (lane >> 2), piece = lane & 3;
+            *reinterpret_cast<uint4*>(stg + rr * 80 + piece * 16) =
+                *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(plane) + ((pix + rr) * p.M + cbase) * 2 + piece * 16);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] += __uint_as_float((uint32_t)*reinterpret_cast<const uint16_t*>(stg + j * 80 + lane * 2) << 16);
+          __syncwarp();
+        };
+        if (p.mode == GEMM_PLANES_ADD_RELU) { rows_in(p.res_hi); rows_in(p.res_lo); }
+        if (p.mode == GEMM_PLANES_RELU || p.mode == GEMM_PLANES_ADD_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        auto rows_out = [&](uint16_t* plane, bool low) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
+            const __nv_bfloat16 o = low ? __float2bfloat16_rn(v[j] - __bfloat162float(h)) : h;
+            *reinterpret_cast<uint16_t*>(stg + j * 80 + lane * 2) = __bfloat16_as_ushort(o);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + (lane >> 2), piece = lane & 3;
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(plane) + ((pix + rr) * p.M + cbase) * 2 + piece * 16) =
+                *reinterpret_cast<const uint4*>(stg + rr * 80 + piece * 16);
+          }
+          __syncwarp();
+        };
+        rows_out(p.out_hi, false);
+        rows_out(p.out_lo, true);
+      };
+
       auto process = [&](uint32_t (&v32)[32], int c0) {
+        if constexpr (kSwap) { process_swapped(v32, c0); return; }
         const int n = n0 + c0;
         float v[32];
 #pragma unroll
@@ -347,17 +412,22 @@ cudaError_t launch_vit_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, co
                             const CUtensorMap& w_lo, const GemmParams& p, int num_sms, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(vit_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(vit_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(vit_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   if (p.M <= 0) return cudaSuccess;
   const int bn = p.bn > 0 ? p.bn : kBN;
   if ((bn != 128 && bn != 192 && bn != 256) || p.N % bn != 0 || p.K % kBlockK != 0) return cudaErrorInvalidValue;
-  if (p.conv && (p.Wo <= 0 || 128 % p.Wo != 0 || p.M % kBM != 0 || p.cblocks <= 0)) return cudaErrorInvalidValue;
+  const int tile_pixels = p.swap ? bn : kBM;
+  if (p.conv && (p.Wo <= 0 || tile_pixels % p.Wo != 0 || p.M % kBM != 0 || p.cblocks <= 0)) return cudaErrorInvalidValue;
+  if (p.swap && (bn != kBN || p.M % kBM != 0 || (p.mode != GEMM_PLANES && p.mode != GEMM_PLANES_RELU && p.mode != GEMM_PLANES_ADD_RELU)))
+    return cudaErrorInvalidValue;
   const int tiles = ((p.M + kBM - 1) / kBM) * (p.N / bn);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  vit_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(a_hi, a_lo, w_hi, w_lo, p);
+  if (p.swap) vit_gemm_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(a_hi, a_lo, w_hi, w_lo, p);
+  else vit_gemm_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(a_hi, a_lo, w_hi, w_lo, p);
   return cudaGetLastError();
 }
 
