@@ -6,7 +6,7 @@ tail -c 3000 gpurun_out/bench.json
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --profile-range > gpurun_out/bench_ncu.log 2>&1
 if [ -n "$KERNEL" ]; then
-ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:$KERNEL -c ${KCOUNT:-1} -o gpurun_out/prof_$KERNEL -f \
+ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:$KERNEL --launch-skip ${KSKIP:-0} -c ${KCOUNT:-1} -o gpurun_out/prof_$KERNEL -f \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --profile-range > gpurun_out/bench_ncu_full.log 2>&1
 fi
 ls -la gpurun_out
