@@ -170,6 +170,7 @@ struct GemmParams {
   // implicit-GEMM convolution (conv != 0): A is an NHWC plane read through a 4-D tensor map, one k-block per
   // (filter tap, 32-channel block); a 128-row tile is 128 / Wo whole output rows of one image
   int conv, Ho, Wo, stride, pad, kw, cblocks;
+  int pair;                   // 2-CTA clusters: 256 x bn tiles through tcgen05 cta_group::2 (W maps must have bn/2-row boxes)
   int swap;                   // rows of C = output channels (M = cout, a [cout, K] filter bank as the 128-row operand),
                               // columns = output pixels (N); outputs are still written as NHWC planes [N, M]
   const uint16_t *res_hi, *res_lo;   // GEMM_PLANES_ADD_RELU: shortcut planes [M,N]

@@ -19,7 +19,8 @@ namespace {
 
 constexpr int kBlockK = 32;
 constexpr int kRowBytes = kBlockK * 2;            // 64 B rows, SWIZZLE_64B
-constexpr int kStages = 4;
+constexpr int kStages = 4;                        // 48 KB stages; CTA pairs: 6 stages of 32 KB (each CTA holds half of W)
+constexpr int kPairStages = 6, kMaxStages = 6;
 constexpr int kBM = 128, kBN = 256;
 constexpr int kAPlane = kBM * kRowBytes;          // 8 KB
 constexpr int kWPlane = kBN * kRowBytes;          // 16 KB
@@ -31,8 +32,8 @@ struct __align__(8) GemmSmemTail {
   float bias_s[2][kBN];                           // per-tile bias / LayerScale columns, double buffered with the accumulator
   float gamma_s[2][kBN];
   uint8_t stage_buf[kEpiWarps][32 * 80];          // per-warp transposition buffer: 32 rows x (64 B + 16 B pad)
-  uint64_t full_bar[kStages];
-  uint64_t empty_bar[kStages];
+  uint64_t full_bar[kMaxStages];
+  uint64_t empty_bar[kMaxStages];
   uint64_t tmem_full_bar[2];
   uint64_t tmem_empty_bar[2];
   uint32_t tmem_base;
@@ -70,33 +71,49 @@ __device__ long long g_gemm_stamp[64];
 // filter bank [128, K] and the 256-row operand is a tile of 256 output pixels, so that the tensor pipe still runs
 // M=128 x N=256 instructions (an N=128 instruction re-reads its operands from shared memory twice as often per FLOP
 // and is limited by shared-memory bandwidth); the epilogue transposes the [channel, pixel] accumulator back to NHWC.
-template <bool kSwap>
+// kPair = true: two CTAs of a cluster (the two SMs of a TPC) share one 256 x bn tile through `tcgen05.mma.cta_group::2`:
+// each CTA stages its own 128 rows of A and bn/2 rows of W, the even CTA issues the M = 256 instructions, every CTA
+// drains its own 128 accumulator rows.  Per SM the tensor core then reads 4 KB + 4 KB of operands per 128-cycle
+// instruction instead of 4 KB + 8 KB, which is what the shared-memory pipe could not sustain next to the epilogue.
+template <bool kSwap, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  static_assert(!(kSwap && kPair), "the swapped layers have M = 128 filters: nothing to pair");
+  constexpr int kNumStages = kPair ? kPairStages : kStages;
+  constexpr int kStageSz = kPair ? 2 * kAPlane + kWPlane : kStageBytes;       // 32 KB / 48 KB
+  constexpr int kWLoOff = 2 * kAPlane + (kPair ? kWPlane / 2 : kWPlane);
+  constexpr int kTileM = kPair ? 2 * kBM : kBM;
   GemmSmemTail& tail = *reinterpret_cast<GemmSmemTail*>(smem + kStages * kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int passes = p.passes;
   const int bn = p.bn > 0 ? p.bn : kBN;                     // 128 / 192 / 256 output columns per tile
-  const uint32_t idesc = umma_idesc_f16(kBM, bn, 1);
-  const int num_m = (p.M + kBM - 1) / kBM, num_n = p.N / bn;
+  const uint32_t idesc = umma_idesc_f16(kTileM, bn, 1);
+  const int num_m = (p.M + kTileM - 1) / kTileM, num_n = p.N / bn;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;     // 0 = leader of the pair
+  const int first_tile = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int num_tiles = num_m * num_n;
   const int num_kb = p.K / kBlockK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&tail.full_bar[s], 1); mbar_init(&tail.empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tail.tmem_full_bar[a], 1); mbar_init(&tail.tmem_empty_bar[a], kEpiWarps); }
+    for (int s = 0; s < kNumStages; ++s) { mbar_init(&tail.full_bar[s], 1); mbar_init(&tail.empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tail.tmem_full_bar[a], 1);
+      mbar_init(&tail.tmem_empty_bar[a], kPair ? 2 * kEpiWarps : kEpiWarps);   // pair: both CTAs' epilogues report to the leader
+    }
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_w_hi);
     if (passes == 3) { tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_w_lo); }
   }
-  if (warp == 2) tmem_alloc(&tail.tmem_base, 512);
+  if (warp == 2) { if constexpr (kPair) tmem_alloc_pair(&tail.tmem_base, 512); else tmem_alloc(&tail.tmem_base, 512); }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();         // barriers and TMEM of the peer exist before anything reaches across
   tc_fence_after();
   const uint32_t tmem_base = tail.tmem_base;
   if (threadIdx.x == 0) GSTAMP(63);
@@ -104,17 +121,18 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx = (passes == 3 ? 2 : 1) * (kAPlane + bn * kRowBytes);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      // pair: each CTA loads 128 rows of A + bn/2 rows of W; all bytes of both CTAs are counted on the leader's barrier
+      const uint32_t tx = (passes == 3 ? 2 : 1) * (kPair ? 2 * (kAPlane + (bn >> 1) * kRowBytes) : kAPlane + bn * kRowBytes);
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         int mt, nt;
         tile_coords(tile, num_m, num_n, mt, nt);
-        const int m0 = mt * kBM, n0 = nt * bn;
+        const int m0 = mt * kTileM + (int)rank * kBM, n0 = nt * bn + (kPair ? (int)rank * (bn >> 1) : 0);
         int img = 0, y0 = 0;
         if (p.conv) { const int hw = p.Ho * p.Wo, pix0 = kSwap ? n0 : m0; img = pix0 / hw; y0 = (pix0 - img * hw) / p.Wo; }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&tail.empty_bar[stage], phase ^ 1);
-          uint8_t* st = smem + stage * kStageBytes;
-          mbar_arrive_expect_tx(&tail.full_bar[stage], tx);
+          uint8_t* st = smem + stage * kStageSz;
+          if (!kPair || rank == 0) mbar_arrive_expect_tx(&tail.full_bar[stage], tx);
           // the pixel operand (A, or W when kSwap) of a convolution: k-block = (tap ky,kx ; 32-channel block cb), a
           // shifted, strided window of the NHWC plane; the other operand is a plain [rows, K] matrix
           int cb = 0, cx = 0, cy = 0;
@@ -124,28 +142,36 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             const int ky = tap / p.kw, kx = tap - ky * p.kw;
             cx = kx - p.pad; cy = y0 * p.stride + ky - p.pad;
           }
+          auto load2 = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
+            if constexpr (kPair) tma_load_2d_pair(dst, map, &tail.full_bar[stage], c0, c1);
+            else tma_load_2d(dst, map, &tail.full_bar[stage], c0, c1);
+          };
+          auto load4 = [&](void* dst, const CUtensorMap* map) {
+            if constexpr (kPair) tma_load_4d_pair(dst, map, &tail.full_bar[stage], cb * kBlockK, cx, cy, img);
+            else tma_load_4d(dst, map, &tail.full_bar[stage], cb * kBlockK, cx, cy, img);
+          };
           if (p.conv && !kSwap) {
-            tma_load_4d(st, &tm_a_hi, &tail.full_bar[stage], cb * kBlockK, cx, cy, img);
-            if (passes == 3) tma_load_4d(st + kAPlane, &tm_a_lo, &tail.full_bar[stage], cb * kBlockK, cx, cy, img);
+            load4(st, &tm_a_hi);
+            if (passes == 3) load4(st + kAPlane, &tm_a_lo);
           } else {
-            tma_load_2d(st, &tm_a_hi, &tail.full_bar[stage], kb * kBlockK, m0);
-            if (passes == 3) tma_load_2d(st + kAPlane, &tm_a_lo, &tail.full_bar[stage], kb * kBlockK, m0);
+            load2(st, &tm_a_hi, kb * kBlockK, m0);
+            if (passes == 3) load2(st + kAPlane, &tm_a_lo, kb * kBlockK, m0);
           }
           if (p.conv && kSwap) {
-            tma_load_4d(st + 2 * kAPlane, &tm_w_hi, &tail.full_bar[stage], cb * kBlockK, cx, cy, img);
-            if (passes == 3) tma_load_4d(st + 2 * kAPlane + kWPlane, &tm_w_lo, &tail.full_bar[stage], cb * kBlockK, cx, cy, img);
+            load4(st + 2 * kAPlane, &tm_w_hi);
+            if (passes == 3) load4(st + kWLoOff, &tm_w_lo);
           } else {
-            tma_load_2d(st + 2 * kAPlane, &tm_w_hi, &tail.full_bar[stage], kb * kBlockK, n0);
-            if (passes == 3) tma_load_2d(st + 2 * kAPlane + kWPlane, &tm_w_lo, &tail.full_bar[stage], kb * kBlockK, n0);
+            load2(st + 2 * kAPlane, &tm_w_hi, kb * kBlockK, n0);
+            if (passes == 3) load2(st + kWLoOff, &tm_w_lo, kb * kBlockK, n0);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kNumStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       int stage = 0; uint32_t phase = 0, unit = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++unit) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++unit) {
         const uint32_t acc = unit & 1u;
         mbar_wait(&tail.tmem_empty_bar[acc], ((unit >> 1) & 1u) ^ 1u);
         tc_fence_after();
@@ -154,22 +180,25 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&tail.full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t st = smem_u32(smem + stage * kStageBytes);
-          const uint32_t a_hi = st, a_lo = st + kAPlane, w_hi = st + 2 * kAPlane, w_lo = st + 2 * kAPlane + kWPlane;
+          const uint32_t st = smem_u32(smem + stage * kStageSz);
+          const uint32_t a_hi = st, a_lo = st + kAPlane, w_hi = st + 2 * kAPlane, w_lo = st + kWLoOff;
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
             if (pass < passes) {
               const uint32_t a = (pass == 2 ? a_lo : a_hi), w = (pass == 1 ? w_lo : w_hi);
 #pragma unroll
-              for (int k16 = 0; k16 < kBlockK / 16; ++k16)
-                umma_f16(d, umma_desc_kmajor<kRowBytes>(a + k16 * 32), umma_desc_kmajor<kRowBytes>(w + k16 * 32), idesc,
-                         (kb | pass | k16) != 0 ? 1u : 0u);
+              for (int k16 = 0; k16 < kBlockK / 16; ++k16) {
+                const uint64_t da = umma_desc_kmajor<kRowBytes>(a + k16 * 32), dw = umma_desc_kmajor<kRowBytes>(w + k16 * 32);
+                const uint32_t accum = (kb | pass | k16) != 0 ? 1u : 0u;
+                if constexpr (kPair) umma_f16_pair(d, da, dw, idesc, accum);
+                else umma_f16(d, da, dw, idesc, accum);
+              }
             }
           }
-          umma_commit(&tail.empty_bar[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if constexpr (kPair) umma_commit_pair(&tail.empty_bar[stage]); else umma_commit(&tail.empty_bar[stage]);
+          if (++stage == kNumStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tail.tmem_full_bar[acc]);
+        if constexpr (kPair) umma_commit_pair(&tail.tmem_full_bar[acc]); else umma_commit(&tail.tmem_full_bar[acc]);
         GSTAMP(unit * 4 + 1);
       }
     }
@@ -178,11 +207,11 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const int r = q * 32 + lane;
     const int etid = e * 32 + lane;
     uint32_t unit = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++unit) {
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++unit) {
       const uint32_t acc = unit & 1u;
       int mt, nt;
       tile_coords(tile, num_m, num_n, mt, nt);
-      const int m = mt * kBM + r;
+      const int m = mt * kTileM + (int)rank * kBM + r;
       const int ntile0 = nt * bn;
       const int half_cols = bn >> 1;                   // columns per epilogue warp: 64 / 96 / 128
       const int n0 = ntile0 + ch * half_cols;
@@ -369,7 +398,10 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       auto release_acc = [&]() {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tail.tmem_empty_bar[acc]);
+        if (lane == 0) {
+          if constexpr (kPair) mbar_arrive_cluster(&tail.tmem_empty_bar[acc], 0);
+          else mbar_arrive(&tail.tmem_empty_bar[acc]);
+        }
       };
       tmem_ld_32x32(taddr, va);
       tmem_ld_wait_for(va);
@@ -400,9 +432,10 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();         // the leader's UMMAs / commits reach into the peer until here
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (kPair) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -412,8 +445,9 @@ cudaError_t launch_vit_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, co
                             const CUtensorMap& w_lo, const GemmParams& p, int num_sms, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(vit_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(vit_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(vit_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(vit_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(vit_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -422,12 +456,25 @@ cudaError_t launch_vit_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, co
   if ((bn != 128 && bn != 192 && bn != 256) || p.N % bn != 0 || p.K % kBlockK != 0) return cudaErrorInvalidValue;
   const int tile_pixels = p.swap ? bn : kBM;
   if (p.conv && (p.Wo <= 0 || tile_pixels % p.Wo != 0 || p.M % kBM != 0 || p.cblocks <= 0)) return cudaErrorInvalidValue;
-  if (p.swap && (bn != kBN || p.M % kBM != 0 || (p.mode != GEMM_PLANES && p.mode != GEMM_PLANES_RELU && p.mode != GEMM_PLANES_ADD_RELU)))
+  if (p.swap && (p.pair || bn != kBN || p.M % kBM != 0 ||
+                 (p.mode != GEMM_PLANES && p.mode != GEMM_PLANES_RELU && p.mode != GEMM_PLANES_ADD_RELU)))
     return cudaErrorInvalidValue;
+  if (p.pair) {                                   // one 2-CTA cluster per 256 x bn tile
+    if (p.conv && p.M % (2 * kBM) != 0) return cudaErrorInvalidValue;
+    const int tiles = ((p.M + 2 * kBM - 1) / (2 * kBM)) * (p.N / bn);
+    const int clusters = tiles < num_sms / 2 ? tiles : num_sms / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, vit_gemm_kernel<false, true>, a_hi, a_lo, w_hi, w_lo, p);
+  }
   const int tiles = ((p.M + kBM - 1) / kBM) * (p.N / bn);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  if (p.swap) vit_gemm_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(a_hi, a_lo, w_hi, w_lo, p);
-  else vit_gemm_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(a_hi, a_lo, w_hi, w_lo, p);
+  if (p.swap) vit_gemm_kernel<true, false><<<grid, kThreads, kSmemBytes, stream>>>(a_hi, a_lo, w_hi, w_lo, p);
+  else vit_gemm_kernel<false, false><<<grid, kThreads, kSmemBytes, stream>>>(a_hi, a_lo, w_hi, w_lo, p);
   return cudaGetLastError();
 }
 
