@@ -417,13 +417,20 @@ def main():
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
 
-    # end to end through the plugin call, host buffers
+    # end to end through the plugin calls, host buffers: every step uploads its own inputs from pinned memory
+    # (`stage`: copy stream, overlapping the previous step's kernels) and reads its own poses + scores back.
+    # All `steps` uploads and read-backs are inside the timed region; only the first upload has nothing to overlap with.
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        poses, scores = step_e2e()
+    staged = model.stage(batch_host, "synthetic")
+    for i in range(args.steps):
+        cur = staged
+        if i + 1 < args.steps:
+            staged = model.stage(batch_host, "synthetic")
+        pred_e2e = model.retrieve(cur, "synthetic")
+        poses, scores = pred_e2e.pred_poses.cpu(), pred_e2e.scores.cpu()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     h2d = sum(batch_host._tensors[k].numel() * batch_host._tensors[k].element_size() for k in ("tar_img", "tar_mask", "tar_K", "tar_M"))

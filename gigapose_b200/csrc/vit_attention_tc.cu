@@ -3,14 +3,16 @@
 // One CTA per (crop, head).  K and V of the head (272 key rows: 257 + padding) are TMA-staged once into shared
 // memory as bf16 hi/lo planes (SWIZZLE_128B, 128-byte rows); the 257 query rows go through in three 128-row tiles:
 //   S = Q K^T          tcgen05.mma SS, M=128, N=256+16, K=64      (A = Q tile, B = K, both K-major)   -> TMEM [0,272)
-//   softmax            128 threads, one query row each: tcgen05.ld S, fp32 max / expf / sum; P is written back to TMEM
-//                      as packed bf16 pairs (hi over the S columns already consumed, lo next to it)
+//   softmax            256 threads, two per query row (keys [0,128) and [128,257); the two warps of a TMEM lane quarter
+//                      exchange row max / row sum through shared memory): tcgen05.ld S, fp32 max / ex2 / sum; P is
+//                      written back to TMEM as packed bf16 pairs (hi over the first 16 columns of the 32-column S
+//                      chunk it came from -- already consumed by the same thread -- lo next to S)
 //   O = P V            tcgen05.mma TS, M=128, N=64, K=272          (A = P from TMEM, B = V as MN-major operand)
 //   epilogue           tcgen05.ld O, divide by the row sum, store bf16 hi/lo planes (A operand of the proj GEMM)
 // Both products use the fp32-faithful split: S = Qh Kh + Qh Kl + Ql Kh, O = Ph Vh + Ph Vl + Pl Vh.
 // The 257th query row (token 256) would cost a third 128-row tile; one extra warp computes it with fp32 FMAs from the
 // same shared-memory K / V planes while the tensor pipeline runs.
-// Warp roles: warp 0 TMA producer (+ TMEM alloc), warp 1 UMMA issuer, warps 2-5 softmax / epilogue, warp 6 last row.
+// Warp roles: warp 0 TMA producer (+ TMEM alloc), warp 1 UMMA issuer, warps 2-9 softmax / epilogue, warp 10 last row.
 #include "gigapose_kernels.h"
 #include "common.cuh"
 #include <cuda_bf16.h>
@@ -25,8 +27,10 @@ constexpr int kRow = 128;                          // bytes per smem row (64 bf1
 constexpr int kKVPlane = kKeys * kRow;             // 34 KB
 constexpr int kQPlane = 128 * kRow;                // 16 KB
 constexpr int kQTiles = 2;                         // tokens 0..255 on the tensor path; token 256 on one SIMT warp
-constexpr int kThreads = 7 * 32;
-// TMEM columns: S [0,288) (the MMAs write [0,272); P_hi later overwrites [0,144)), P_lo [288,432), O [432,496)
+constexpr int kSoftmaxWarps = 8;
+constexpr int kThreads = (2 + kSoftmaxWarps + 1) * 32;
+// TMEM columns: S [0,288) (the MMAs write [0,272); P_hi of keys [32c,32c+32) later overwrites columns [32c,32c+16)),
+// P_lo [288,432), O [432,496)
 constexpr uint32_t kColS = 0, kColPlo = 288, kColO = 432;
 constexpr uint32_t kIdescS256 = umma_idesc_f16(128, 256, 1);
 constexpr uint32_t kIdescS16 = umma_idesc_f16(128, 16, 1);
@@ -38,9 +42,6 @@ struct __align__(8) AttnTail {
 };
 constexpr int kSmem = 1024 + 4 * kKVPlane + 4 * kQPlane + sizeof(AttnTail);
 
-__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-}
 // (a, b) -> packed bf16x2 hi word (a in the low half) and the bf16x2 of the residuals: 6 instructions per pair
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
@@ -66,9 +67,9 @@ __device__ __forceinline__ float2 ld_pair_sw128(const uint8_t* hi, const uint8_t
 
 }  // namespace
 
-// cycle stamps of CTA 0 (diagnostics: gp_debug_attention_timeline)
+// cycle stamps of CTA 300 (a warm, second-wave CTA; CTA 0 for small grids) (diagnostics: gp_debug_attention_timeline)
 __device__ long long g_attn_stamp[32];
-#define STAMP(i) do { if (blockIdx.x == 0) g_attn_stamp[i] = clock64(); } while (0)
+#define STAMP(i) do { if (blockIdx.x == (gridDim.x > 300 ? 300u : 0u)) g_attn_stamp[i] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(kThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_constant__ CUtensorMap tm_lo_128,
@@ -94,7 +95,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
     mbar_init(&tail.v_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&tail.q_full[i], 1); mbar_init(&tail.q_empty[i], 1); }
     mbar_init(&tail.s_full, 1);
-    mbar_init(&tail.p_ready, 4);
+    mbar_init(&tail.p_ready, kSoftmaxWarps);
     mbar_init(&tail.o_full, 1);
     fence_barrier_init();
   }
@@ -175,7 +176,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
         STAMP(3 + 4 * qt);
 #pragma unroll
         for (int j = 0; j < kKeys / 16; ++j) {         // 17 key steps
-          const uint32_t ph = tmem + kColS + 8 * j, pl = tmem + kColPlo + 8 * j;
+          const uint32_t ph = tmem + kColS + 32 * (j >> 1) + 8 * (j & 1), pl = tmem + kColPlo + 8 * j;   // keys 16j..16j+15
           const uint64_t dvh = umma_desc_mnmajor_sw128(vh + j * 16 * kRow), dvl = umma_desc_mnmajor_sw128(vl + j * 16 * kRow);
           umma_f16_ts(tmem + kColO, ph, dvh, kIdescPV, j != 0 ? 1u : 0u);
           if (passes == 3) {
@@ -187,36 +188,47 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
         STAMP(4 + 4 * qt);
       }
     }
-  } else if (warp < 6) {
-    // ============================== softmax + epilogue (warps 2-5) ==============================
+  } else if (warp < 2 + kSoftmaxWarps) {
+    // ============================== softmax + epilogue (warps 2-9) ==============================
+    // warps w and w+4 share a TMEM lane quarter (w & 3): the same 32 query rows, key columns split in two halves
+    __shared__ float s_mx[2][128];
+    __shared__ float s_sum[2][128];
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                  // 0: keys [0,128)   1: keys [128,257)
     const int r = quarter * 32 + lane;                 // query row inside the tile
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const uint32_t s_base = tmem + lane_base + kColS + 128 * half;
     for (int qt = 0; qt < kQTiles; ++qt) {
       const int tok = qt * 128 + r;
       const bool row_ok = tok < kTok;
       mbar_wait(&tail.s_full, qt & 1);
       tc_fence_after();
       if (warp == 2 && lane == 0) STAMP(12 + 5 * qt);
-      // pass 1: row maximum of the raw logits over the 257 real keys: 8 full chunks of 32 columns + column 256
+      // pass 1: maximum of the raw logits over this half's keys (4 chunks of 32 columns; + column 256 in half 1)
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem + lane_base + kColS + 32 * c, v);
+        tmem_ld_32x32(s_base + 32 * c, v);
         tmem_ld_wait_for(v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
       }
-      uint32_t tailv[32];                              // columns [256,288): only key 256 is real
-      tmem_ld_32x32(tmem + lane_base + kColS + 256, tailv);
-      tmem_ld_wait_for(tailv);
-      mx = fmaxf(mx, __uint_as_float(tailv[0]));
+      float tail_logit = -INFINITY;                    // key 256 (columns [256,288): only the first is real)
+      if (half == 1) {
+        uint32_t tailv[32];
+        tmem_ld_32x32(tmem + lane_base + kColS + 256, tailv);
+        tmem_ld_wait_for(tailv);
+        tail_logit = __uint_as_float(tailv[0]);
+        mx = fmaxf(mx, tail_logit);
+      }
+      s_mx[half][r] = mx;
+      named_barrier_sync(1 + quarter, 64);
+      mx = fmaxf(mx, s_mx[half ^ 1][r]);
       if (warp == 2 && lane == 0) STAMP(13 + 5 * qt);
-      // pass 2: p = exp((s - max) / 8) via ex2; P goes back to TMEM as packed bf16 pairs (hi over S columns already
-      // consumed, lo next to S); row sum in fp32
+      // pass 2: p = exp((s - max) / 8) via ex2; P goes back to TMEM as packed bf16 pairs; row sum in fp32
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-      auto do_chunk = [&](uint32_t (&v)[32], int c) {
+      auto do_chunk = [&](uint32_t (&v)[32], int c) {   // c = chunk inside this half; keys 128*half + 32c ..
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -225,47 +237,50 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
           sum4[j & 3] += pa + pb;
           split_pair(pa, pb, hi[j], lo[j]);
         }
-        tmem_st_32x16(tmem + lane_base + kColS + 16 * c, hi);       // columns [16c,16c+16) < 32c+32: already read
-        tmem_st_32x16(tmem + lane_base + kColPlo + 16 * c, lo);
+        tmem_st_32x16(s_base + 32 * c, hi);            // first 16 columns of the chunk just read
+        tmem_st_32x16(tmem + lane_base + kColPlo + 64 * half + 16 * c, lo);
       };
-      {   // software-pipelined: chunk c+1 is in flight while chunk c is processed (it is read before the P store of
-          // chunk c can touch it: P columns of chunk c end at 16c+16 <= 32(c+1))
+      {   // software-pipelined: chunk c+1 is in flight while chunk c is processed (the P store of chunk c only touches
+          // chunk c's own columns)
         uint32_t va[32], vb[32];
-        tmem_ld_32x32(tmem + lane_base + kColS, va);
+        tmem_ld_32x32(s_base, va);
         tmem_ld_wait_for(va);
 #pragma unroll
-        for (int c = 0; c < 8; c += 2) {
-          tmem_ld_32x32(tmem + lane_base + kColS + 32 * (c + 1), vb);      // in flight during chunk c
+        for (int c = 0; c < 4; c += 2) {
+          tmem_ld_32x32(s_base + 32 * (c + 1), vb);      // in flight during chunk c
           do_chunk(va, c);
           tmem_ld_wait_for(vb);
-          if (c + 2 < 8) tmem_ld_32x32(tmem + lane_base + kColS + 32 * (c + 2), va);   // in flight during chunk c+1
+          if (c + 2 < 4) tmem_ld_32x32(s_base + 32 * (c + 2), va);   // in flight during chunk c+1
           do_chunk(vb, c + 1);
-          if (c + 2 < 8) tmem_ld_wait_for(va);
+          if (c + 2 < 4) tmem_ld_wait_for(va);
         }
       }
       float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-      {
+      if (half == 1) {
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) { hi[j] = 0u; lo[j] = 0u; }
-        const float pa = ex2_approx((__uint_as_float(tailv[0]) - mx) * kExpScale);
+        const float pa = ex2_approx((tail_logit - mx) * kExpScale);
         sum += pa;
         split_pair(pa, 0.f, hi[0], lo[0]);
-        tmem_st_32x16(tmem + lane_base + kColS + 128, hi);          // keys 256..287 (271 used): columns [128,144)
+        tmem_st_32x16(tmem + lane_base + kColS + 256, hi);          // keys 256..287 (271 used)
         tmem_st_32x16(tmem + lane_base + kColPlo + 128, lo);
       }
+      s_sum[half][r] = sum;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail.p_ready);
+      named_barrier_sync(1 + quarter, 64);               // partner's partial sum is in shared memory
+      sum += s_sum[half ^ 1][r];
       if (warp == 2 && lane == 0) STAMP(14 + 5 * qt);
-      // epilogue: O / sum -> bf16 hi/lo planes
+      // epilogue: O / sum -> bf16 hi/lo planes; this warp stores output columns [32*half, 32*half + 32)
       mbar_wait(&tail.o_full, qt & 1);
       tc_fence_after();
       if (warp == 2 && lane == 0) STAMP(15 + 5 * qt);
       const float inv = 1.0f / sum;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      {
+        const int c = half;
         uint32_t v[32];
         tmem_ld_32x32(tmem + lane_base + kColO + 32 * c, v);
         tmem_ld_wait_for(v);

@@ -170,6 +170,26 @@ class GigaPose(LightningModule):
         graph.replay()
         return out
 
+    def stage(self, batch, dataset_name):
+        """Start the host->device copy of a (pinned) batch on a dedicated copy stream and return the device-resident
+        batch; `retrieve` waits for the copy.  Staging batch i+1 before retrieving batch i overlaps its upload with
+        batch i's kernels (what a DataLoader with `pin_memory` + a prefetching trainer loop does for the reference)."""
+        if dataset_name not in self.engines:
+            self.set_template_data(dataset_name)
+        device = self.engines[dataset_name].device
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=device)
+        with torch.cuda.stream(self._copy_stream):
+            staged = tc.PandasTensorCollection(infos=batch.infos, **{k: v.to(device, non_blocking=True)
+                                                                     for k, v in batch._tensors.items()})
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        staged._ready = ready
+        for name in ("test_list",):
+            if hasattr(batch, name):
+                setattr(staged, name, getattr(batch, name))
+        return staged
+
     @torch.no_grad()
     def retrieve(self, batch, dataset_name):
         """Rows a1, a3-a9 for one batch; returns the PandasTensorCollection `eval_retrieval` builds."""
@@ -177,6 +197,12 @@ class GigaPose(LightningModule):
             self.set_template_data(dataset_name)
         eng = self.engines[dataset_name]
         device = eng.device
+        ready = getattr(batch, "_ready", None)
+        if ready is not None:                            # staged batch: its upload ran on the copy stream
+            cur = torch.cuda.current_stream(device)
+            cur.wait_event(ready)
+            for t in batch._tensors.values():
+                t.record_stream(cur)
         tar_img = batch.tar_img.to(device, non_blocking=True)
         tar_mask = batch.tar_mask.to(device, non_blocking=True)
         q_obj = torch.as_tensor(np.asarray(batch.infos.label).astype(np.int64) - 1, device=device)   # gigaPose.py:514-520

@@ -126,6 +126,15 @@ def test_gigapose_module_end_to_end_small():
     # oracle for the matching stage on the GPU-computed features of the same crops
     eng = model.engines["synthetic"]
     assert eng.launch_count() > 0
+    # staged (prefetched on the copy stream) batches give the same answer, eagerly and through the CUDA graph
+    for graph in (False, True):
+        model.use_cuda_graph = graph
+        nxt = model.stage(batch, "synthetic")
+        for _ in range(3):
+            cur, nxt = nxt, model.stage(batch, "synthetic")
+            again = model.retrieve(cur, "synthetic")
+            assert torch.equal(again.id_src.cpu(), pred.id_src.cpu())
+            assert torch.equal(again.pred_poses.cpu(), pred.pred_poses.cpu())
 
 
 @pytest.mark.parametrize("backend,tol", [("native", 3e-4), ("cudnn", 3e-3)])
