@@ -24,6 +24,17 @@ from src.utils.logging import get_logger
 logger = get_logger(__name__)
 
 
+class _HostResult:
+    """Pinned host copies of one batch's `pred_poses` / `scores`, valid after `result()` returned."""
+
+    def __init__(self, poses, scores, done):
+        self._poses, self._scores, self._done = poses, scores, done
+
+    def result(self):
+        self._done.synchronize()
+        return self._poses, self._scores
+
+
 class GigaPose(LightningModule):
     def __init__(self, model_name, ae_net, ist_net, training_loss, testing_metric, optim_config, log_interval, log_dir,
                  max_num_dets_per_forward=None, test_setting="localization", **kwargs):
@@ -182,6 +193,9 @@ class GigaPose(LightningModule):
         with torch.cuda.stream(self._copy_stream):
             staged = tc.PandasTensorCollection(infos=batch.infos, **{k: v.to(device, non_blocking=True)
                                                                      for k, v in batch._tensors.items()})
+            labels = torch.from_numpy(np.asarray(batch.infos.label).astype(np.int64) - 1).pin_memory()
+            staged._q_obj = labels.to(device, non_blocking=True)          # object indices (gigaPose.py:514-520)
+            staged._q_obj_host = labels                                    # keeps the pinned source alive until the copy ran
             ready = torch.cuda.Event()
             ready.record(self._copy_stream)
         staged._ready = ready
@@ -189,6 +203,26 @@ class GigaPose(LightningModule):
             if hasattr(batch, name):
                 setattr(staged, name, getattr(batch, name))
         return staged
+
+    def fetch_async(self, predictions):
+        """Enqueue the device->host copy of a batch's poses and scores (pinned ring buffers, current stream) and return
+        a handle whose `.result()` waits for it: the caller can launch the next batch before reading this one."""
+        ring = getattr(self, "_host_ring", None)
+        if ring is None:
+            ring = self._host_ring = {"slot": 0, "bufs": {}}
+        ring["slot"] = (ring["slot"] + 1) % 3
+        out = []
+        for name in ("pred_poses", "scores"):
+            t = getattr(predictions, name)
+            key = (name, ring["slot"], tuple(t.shape), t.dtype)
+            buf = ring["bufs"].get(key)
+            if buf is None:
+                buf = ring["bufs"][key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            buf.copy_(t, non_blocking=True)
+            out.append(buf)
+        done = torch.cuda.Event()
+        done.record()
+        return _HostResult(out[0], out[1], done)
 
     @torch.no_grad()
     def retrieve(self, batch, dataset_name):
@@ -201,11 +235,14 @@ class GigaPose(LightningModule):
         if ready is not None:                            # staged batch: its upload ran on the copy stream
             cur = torch.cuda.current_stream(device)
             cur.wait_event(ready)
-            for t in batch._tensors.values():
+            for t in list(batch._tensors.values()) + [batch._q_obj]:
                 t.record_stream(cur)
         tar_img = batch.tar_img.to(device, non_blocking=True)
         tar_mask = batch.tar_mask.to(device, non_blocking=True)
-        q_obj = torch.as_tensor(np.asarray(batch.infos.label).astype(np.int64) - 1, device=device)   # gigaPose.py:514-520
+        if ready is not None:
+            q_obj = batch._q_obj                         # uploaded with the batch: no blocking pageable copy here
+        else:
+            q_obj = torch.as_tensor(np.asarray(batch.infos.label).astype(np.int64) - 1, device=device)   # gigaPose.py:514-520
         tar_K, tar_M = batch.tar_K.to(device).float(), batch.tar_M.to(device).float()
         outs = []
         B = tar_img.shape[0]

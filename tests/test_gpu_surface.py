@@ -133,8 +133,11 @@ def test_gigapose_module_end_to_end_small():
         for _ in range(3):
             cur, nxt = nxt, model.stage(batch, "synthetic")
             again = model.retrieve(cur, "synthetic")
+            handle = model.fetch_async(again)
             assert torch.equal(again.id_src.cpu(), pred.id_src.cpu())
-            assert torch.equal(again.pred_poses.cpu(), pred.pred_poses.cpu())
+            poses_host, scores_host = handle.result()
+            assert poses_host.is_pinned() and torch.equal(poses_host, pred.pred_poses.cpu())
+            assert torch.equal(scores_host, pred.scores.cpu())
 
 
 @pytest.mark.parametrize("backend,tol", [("native", 3e-4), ("cudnn", 3e-3)])
