@@ -1,14 +1,20 @@
-// Linear layers of the DINOv2 ViT-L/14 forward on tcgen05 (row a1 of SURVEY.md §8; the hub module the reference
-// calls at ae_net.py:46 runs these as fp32 cuBLAS GEMMs).
+// The tcgen05 GEMM of this library: the linear layers of the DINOv2 ViT-L/14 forward (row a1 of SURVEY.md §8; the hub
+// module the reference calls at ae_net.py:46 runs them as fp32 cuBLAS GEMMs) and, as implicit GEMMs, the convolutions
+// of the IST trunk (row a6, ist_trunk.cu; cuDNN in the reference).
 //
 // C[M,N] = A[M,K] . W[N,K]^T with both operands stored as bf16 hi/lo planes (x = hi + lo to ~2^-17) and accumulated
 // as hi*hi + hi*lo + lo*hi in fp32 TMEM accumulators -- the same fp32-faithful split as the similarity kernel
-// (`passes = 1` = plain bf16).  Persistent CTAs, one 128 x 256 output tile at a time:
-//   warp 0  TMA producer   (A box 128 x 32, W box 256 x 32, SWIZZLE_64B, 4-stage ring)
-//   warp 1  UMMA issuer    (cta_group::1, M=128, N=256, K=16), two TMEM accumulators (2 x 256 columns)
+// (`passes = 1` = plain bf16).  Persistent CTAs, one output tile at a time:
+//   warp 0  TMA producer   (32-column k-blocks, SWIZZLE_64B; A rows = 2-D boxes, or 4-D boxes of an NHWC plane when the
+//                           GEMM is a convolution: one box per filter tap and 32-channel block, zero fill = padding)
+//   warp 1  UMMA issuer    (M=128, N=128..256, K=16), two TMEM accumulators (2 x 256 columns)
 //   warp 2  TMEM allocator
-//   warps 4-11 epilogue    (TMEM -> registers -> fused bias / GELU / LayerScale + residual / positional table ->
-//                           fp32 rows or bf16 hi/lo planes for the next GEMM), overlapping the next tile's MMAs.
+//   warps 4-11 epilogue    (TMEM -> registers -> fused bias / GELU / ReLU / LayerScale + residual / shortcut /
+//                           positional table -> fp32 rows or bf16 hi/lo planes for the next layer), overlapping the
+//                           next tile's MMAs; stores are transposed through shared memory into full 64-byte segments.
+// Three instantiations: <swap=0,pair=0> 128 x bn tiles on one CTA; <0,1> 256 x bn tiles on a 2-CTA cluster
+// (tcgen05 cta_group::2, the ViT linears); <1,0> filters as the 128-row operand against 256 output pixels (the
+// 128-channel convolutions).
 #include "gigapose_kernels.h"
 #include "common.cuh"
 #include <cuda_bf16.h>
