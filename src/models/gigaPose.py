@@ -297,10 +297,6 @@ class GigaPose(LightningModule):
         if self.global_rank != 0:
             return
         prediction_dir = osp.join(self.log_dir, "predictions")
-        try:    # BOP csv writer = row f4 ("next"); present when this package overlays a reference checkout
-            from src.utils.inout import save_predictions_from_batched_predictions
-        except Exception:
-            logger.info(f"per-image predictions are in {prediction_dir}; BOP csv export needs src/utils/inout.py")
-            return
+        from src.utils.inout import save_predictions_from_batched_predictions      # row f4: BOP csv export
         save_predictions_from_batched_predictions(prediction_dir, dataset_name=self.test_dataset_name,
                                                   model_name=self.model_name, run_id=self.run_id, is_refined=False)

@@ -197,3 +197,15 @@ def test_test_step_writes_reference_npz_schema(tmp_path):
     lab = labels.numpy()
     for row, oid in enumerate(data["object_id"]):
         assert np.isclose(data["scores"][row, 0], s0[lab == oid].max())
+    # on_test_epoch_end (gigaPose.py:644-653) turns the per-batch files into the two BOP csv files (row f4)
+    from src.utils import inout
+    model.run_id = "t0"
+    model.on_test_epoch_end()
+    stem = os.path.join(model.log_dir, "predictions", f"{model.model_name}-pbrreal-rgb-mmodel_synthetic-test_t0")
+    top1 = inout.load_bop_results(stem + ".csv")
+    topk = inout.load_bop_results(stem + "MultiHypothesis.csv", additional_name="instance_id")
+    assert len(top1) == n and len(topk) == 5 * n
+    for row, est in enumerate(top1):
+        assert est["obj_id"] == int(data["object_id"][row])
+        assert np.allclose(est["R"], data["poses"][row, 0, :3, :3]) and np.allclose(est["t"][:, 0], data["poses"][row, 0, :3, 3])
+        assert np.isclose(est["time"], 0.25 + data["time"][row])          # detection time + the one batch that held it
