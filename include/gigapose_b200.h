@@ -216,6 +216,21 @@ int gp_ist_trunk_destroy(gp_ist_trunk_handle_t h);
  * ISTNet.forward_by_chunk returns (ist_net.py:52-64), stored patch-major (the layout gp_bank_write / gp_ist_mlp keep). */
 int gp_ist_trunk_forward(gp_ist_trunk_handle_t h, int n, const float* crops, float* feat, void* stream);
 
+/* --- row f3: query pre-processing (CropResizePad.__call__, src/utils/crop.py:16-61, fused with the element-wise steps
+ * of process_real, dataloader/train.py:80-123, and the CLIP normalisation, configs/data/transform.yaml:2-7) ---------- */
+/* For detection i: crop xyxy_boxes[i] (i64 [n,4]; upper bounds clip to the image, negative corners clamp to 0) out of
+ * images[image_index ? image_index[i] : i] (f32 [*,C,H,W]), nearest resize so that the longer box side becomes
+ * target_size, centred zero padding, nearest resize to target_size x target_size -> out_images [n,C,T,T]; out_M [n,3,3]
+ * (may be NULL) is the 3x3 map from image to crop pixels (the `M` GigaPose carries as tar_M / template M).
+ * Optional fused element-wise steps, in the reference's order: value / in_div (255 for 8-bit data, 1 = off), x mask
+ * (f32 [n,H,W] or NULL; its crop goes to out_mask [n,T,T] when that is not NULL), then after the padding
+ * (value - post_sub[c]) / post_div[c] (per channel, NULL = off).  target_size >= 128 (ATen index arithmetic of large
+ * outputs; the shipped configuration uses 224).  Needs no handle. */
+int gp_crop_resize_pad(int n, int channels, int height, int width, int target_size, const float* images,
+                       const int32_t* image_index, const int64_t* xyxy_boxes, const float* mask, float in_div,
+                       const float* post_sub, const float* post_div, float* out_images, float* out_mask, float* out_M,
+                       void* stream);
+
 /* --- diagnostics ----------------------------------------------------------------------------------------- */
 /* number of kernels this library has launched since load (all handles); used for bench.py's `gpu_launches` */
 uint64_t gp_launch_count(void);

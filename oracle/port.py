@@ -422,6 +422,74 @@ class ISTBackbonePort(nn.Module):
 # a3+a4+a5+a7+a8+a9  eval_retrieval sequencing   (gigaPose.py:497-604)
 # ------------------------------------------------------------------------------------------------------------
 @torch.no_grad()
+def crop_resize_pad(xyxy_boxes, images, target_size=224):
+    """Row f3: CPU restatement of `CropResizePad.__call__` (reference src/utils/crop.py:16-61) as explicit index maps.
+
+    xyxy_boxes [n,4] (any integer/float dtype; truncated to int64 as `BoundingBox.convert_long`, bbox.py:18-22),
+    images [n,C,H,W] -> dict(M [n,3,3] f32, images [n,C,target,target]).  Per detection (crop.py:22-55):
+      crop image[:, y1:y2, x1:x2] (python slicing: upper bounds clip to the image);
+      nearest resize by scale = target / max(w_box, h_box) (a float32 tensor value, passed on as a python float):
+        out size floor(size * scale) in double, source index min(floor(dst * float32(1 / scale)), size - 1)
+        (ATen's small-output kernel special-cases unchanged / doubled sizes, see `nearest_map`);
+      if the resized crop is not square: centred zero padding to target x target;
+      nearest resize to (target, target) by size ratio (float32(in / out)): the identity unless a pixel went missing;
+      M = M_resize_pad @ M_crop.
+    """
+    boxes = torch.as_tensor(xyxy_boxes).long()
+    n, C, H, W = images.shape
+    T = int(target_size)
+    out = torch.zeros(n, C, T, T, dtype=images.dtype)
+    Ms = torch.zeros(n, 3, 3, dtype=torch.float32)
+    sizes = torch.stack([boxes[:, 2] - boxes[:, 0], boxes[:, 3] - boxes[:, 1]], dim=-1)
+    scales = T / torch.max(sizes, dim=-1)[0]                               # float32 tensor (crop.py:20)
+    f32 = lambda v: torch.tensor(v, dtype=torch.float32)
+
+    def nearest_map(out_size, in_size, inv, small):
+        # ATen CPU nearest (UpSampleKernel.cpp): source index min(floorf(dst * inv), in - 1) in float32.  Outputs with
+        # out_h + out_w <= 128 go through a second kernel (`_use_vectorized_kernel_cond_2d`) whose `nearest_idx`
+        # special-cases an unchanged size (identity) and an exactly doubled size (dst >> 1); at the shipped target size
+        # 224 that kernel is never selected.
+        dst = torch.arange(out_size)
+        if small and out_size == in_size:
+            return dst
+        if small and out_size == 2 * in_size:
+            return dst >> 1
+        idx = torch.floor(dst.to(torch.float32) * inv).long()
+        return torch.clamp(idx, max=in_size - 1)
+
+    for i in range(n):
+        x1, y1, x2, y2 = (int(v) for v in boxes[i])
+        assert 0 <= x1 < x2 and 0 <= y1 < y2, "boxes need a non-negative top-left corner and positive size"
+        scale = scales[i].item()
+        ch, cw = min(y2, H) - y1, min(x2, W) - x1                          # crop size after slicing
+        rh, rw = int(math.floor(float(ch) * scale)), int(math.floor(float(cw) * scale))
+        inv = f32(1.0 / scale)
+        small = rh + rw <= 128
+        rows, cols = y1 + nearest_map(rh, ch, inv, small), x1 + nearest_map(rw, cw, inv, small)
+        pad_left = pad_top = 0
+        ph, pw = rh, rw
+        if rw / rh != 1:                                                   # crop.py:37-46
+            pad_top = (T - rh) // 2
+            pad_bottom = max(T - rh - pad_top, 0)
+            pad_left = max((T - rw) // 2, 0)
+            pad_right = T - rw - pad_left
+            ph, pw = rh + pad_top + pad_bottom, rw + pad_left + pad_right
+        # final resize to (T, T): padded row / column of every output pixel, then back to crop coordinates
+        prow = nearest_map(T, ph, f32(ph) / f32(T), 2 * T <= 128) - pad_top
+        pcol = nearest_map(T, pw, f32(pw) / f32(T), 2 * T <= 128) - pad_left
+        ok_r, ok_c = (prow >= 0) & (prow < rh), (pcol >= 0) & (pcol < rw)
+        src_r, src_c = rows[prow.clamp(0, rh - 1)], cols[pcol.clamp(0, rw - 1)]
+        patch = images[i][:, src_r][:, :, src_c]
+        out[i] = patch * (ok_r[:, None] & ok_c[None, :]).to(images.dtype)
+        M_crop, M_rp = torch.eye(3), torch.eye(3)
+        M_crop[:2, 2] = -boxes[i, :2].float()
+        M_rp[:2, :2] *= scales[i]
+        if rw / rh != 1:
+            M_rp[:2, 2] = torch.tensor([pad_left, pad_top], dtype=torch.float32)
+        Ms[i] = torch.matmul(M_rp, M_crop)
+    return {"M": Ms, "images": out}
+
+
 def retrieval(ref_inputs, regressor, k=5, sim_threshold=0.5, patch_threshold=3, sub_batch=None):
     """`ref_inputs` = gigapose_b200.synth.to_reference_layout(case): features already extracted (feature-level)."""
     B = ref_inputs["tar_feat"].shape[0]
