@@ -32,7 +32,9 @@ __device__ CropGeom crop_geometry(const long long* box, int H, int W, int T) {
   g.cw = max((int)min(bx2, (long long)W) - g.x1, 0);
   g.ch = max((int)min(by2, (long long)H) - g.y1, 0);
   const long long side = max(box[2] - box[0], box[3] - box[1]);        // the un-clipped box decides the scale (crop.py:19-20)
-  g.scale = (float)T / (float)side;
+  // `target / sizes.max()` on an integer tensor is `sizes.reciprocal() * target` in float32 (Tensor.__rtruediv__): two
+  // roundings, not one division
+  g.scale = __fmul_rn(__frcp_rn((float)side), (float)T);
   const double sd = (double)g.scale;
   g.rh = (int)floor((double)g.ch * sd);
   g.rw = (int)floor((double)g.cw * sd);

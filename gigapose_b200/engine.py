@@ -4,6 +4,7 @@ every arithmetic step below is a kernel of libgigapose_b200.so (no torch fallbac
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional, Sequence
 
 import torch
@@ -127,6 +128,54 @@ class Engine:
         assert K.shape == (self.O, 3, 3) and M.shape == (self.O, self.T_global, 3, 3)
         assert poses.shape == (self.O, self.T_global, 4, 4)
         check(self.lib.gp_bank_set_poses(self._h, K.data_ptr(), M.data_ptr(), poses.data_ptr(), self.stream))
+
+    # ---------------------------------------------------------------------------------------- persistence (row f2)
+    BANK_MAGIC = b"GPB200BANK\x00"
+    BANK_FORMAT = 1
+
+    def _bank_view(self) -> torch.Tensor:
+        off = (-self._bank_mem.data_ptr()) % 1024
+        return self._bank_mem[off:off + self.bank_bytes]
+
+    def _bank_header(self) -> dict:
+        c = self.cfg
+        return dict(format=self.BANK_FORMAT, abi_version=int(c.abi_version), num_objects=self.O, num_templates=self.T,
+                    num_templates_global=self.T_global, template_id_stride=self.shard_world,
+                    template_id_offset=self.shard_rank, precision=self.precision, patch_size=int(c.patch_size),
+                    bank_bytes=int(self.bank_bytes))
+
+    def save_bank(self, path: str) -> None:
+        """Writes the onboarded bank -- descriptor planes, sampled masks, IST features and pose tables exactly as they
+        lie in HBM (the library carves one caller-owned buffer at fixed offsets, so the bytes are position independent)
+        -- behind a small JSON header.  The reference only caches raw template crops
+        (custom_megapose/template_dataset.py:91-119) and re-encodes them at every start (gigaPose.py:357-398)."""
+        import json
+        header = json.dumps(self._bank_header(), sort_keys=True).encode()
+        host = self._bank_view().cpu().numpy()                    # stream-ordered copy + sync
+        tmp = path + ".tmp"
+        with open(tmp, "wb") as f:
+            f.write(self.BANK_MAGIC)
+            f.write(len(header).to_bytes(8, "little"))
+            f.write(header)
+            host.tofile(f)
+        os.replace(tmp, path)
+
+    def load_bank(self, path: str) -> None:
+        """Inverse of `save_bank`; refuses files written for another shape / shard / precision / library ABI."""
+        import json
+        import numpy as np
+        with open(path, "rb") as f:
+            if f.read(len(self.BANK_MAGIC)) != self.BANK_MAGIC:
+                raise _lib.GigaPoseNativeError(f"{path} is not a gigapose_b200 bank file")
+            header = json.loads(f.read(int.from_bytes(f.read(8), "little")))
+            want = self._bank_header()
+            if header != want:
+                diff = {k: (header.get(k), v) for k, v in want.items() if header.get(k) != v}
+                raise _lib.GigaPoseNativeError(f"bank file {path} does not match this engine: {diff}")
+            data = np.fromfile(f, dtype=np.uint8)
+        if data.size != self.bank_bytes:
+            raise _lib.GigaPoseNativeError(f"bank file {path} is truncated: {data.size} of {self.bank_bytes} bytes")
+        self._bank_view().copy_(torch.from_numpy(data))
 
     def set_ist_weights(self, regressor) -> None:
         """`regressor`: module with `scale_predictor` / `inplane_predictor` Sequentials (ist_net.py:140-155)."""

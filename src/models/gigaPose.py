@@ -59,6 +59,7 @@ class GigaPose(LightningModule):
         self.template_datasets = None
         self.test_dataset_name = None
         self.max_dets_per_call = int(kwargs.get("max_dets_per_call", 128))
+        self.bank_cache_dir = kwargs.get("bank_cache_dir", None)         # row f2: on-disk cache of the encoded bank
         self.last_times = {}
         self.profile_stages = False          # bench.py --stage-times: CUDA events between the stages of retrieve()
         self.stage_ms = {}
@@ -90,18 +91,30 @@ class GigaPose(LightningModule):
         start = torch.cuda.Event(enable_timing=True)
         stop = torch.cuda.Event(enable_timing=True)
         start.record()
+        # row f2: with `bank_cache_dir` set, the encoded bank is read back from disk instead of re-running both
+        # backbones over all O x T template crops (the cache is only valid for the weights it was written with)
+        cache = None
+        if getattr(self, "bank_cache_dir", None):
+            os.makedirs(self.bank_cache_dir, exist_ok=True)
+            cache = osp.join(self.bank_cache_dir, f"{dataset_name}_{n_obj}x{T}_{eng.precision}.gpbank")
+        cached = cache is not None and osp.exists(cache)
+        if cached:
+            eng.load_bank(cache)
         for idx in range(n_obj):
             data = first if idx == 0 else dataset[idx]
-            rgb = data.rgb.to(device)
-            tokens = self.ae_net.patch_tokens(rgb)                       # [T,256,1024], normalised once (ae_net.py:69)
-            ist = self.ist_net.forward_by_chunk(rgb)                     # [T,256,16,16]
-            eng.bank_write(idx, 0, tokens, data.mask.to(device), ist_feat=ist, norm_passes=1)   # + matching.py:229
+            if not cached:
+                rgb = data.rgb.to(device)
+                tokens = self.ae_net.patch_tokens(rgb)                   # [T,256,1024], normalised once (ae_net.py:69)
+                ist = self.ist_net.forward_by_chunk(rgb)                 # [T,256,16,16]
+                eng.bank_write(idx, 0, tokens, data.mask.to(device), ist_feat=ist, norm_passes=1)   # + matching.py:229
             Ks.append(data.K.to(device))
             Ms.append(data.M.to(device))
             poses.append(data.poses.to(device))
         K, M, P = torch.stack(Ks).float(), torch.stack(Ms).float(), torch.stack(poses).float()
         eng.set_poses(K, M, P)
         eng.set_ist_weights(self.ist_net.regressor)
+        if cache is not None and not cached:
+            eng.save_bank(cache)
         stop.record()
         stop.synchronize()
         self.engines[dataset_name] = eng

@@ -209,3 +209,43 @@ def test_test_step_writes_reference_npz_schema(tmp_path):
         assert est["obj_id"] == int(data["object_id"][row])
         assert np.allclose(est["R"], data["poses"][row, 0, :3, :3]) and np.allclose(est["t"][:, 0], data["poses"][row, 0, :3, 3])
         assert np.isclose(est["time"], 0.25 + data["time"][row])          # detection time + the one batch that held it
+
+
+def test_bank_persistence_round_trip(tmp_path):
+    """Row f2: the onboarded bank written to disk and read back into a fresh engine gives bit-identical retrieval;
+    files for another shape are refused; `GigaPose(bank_cache_dir=...)` skips the template encoders on the second run."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from gigapose_b200.engine import Engine
+    from gigapose_b200._lib import GigaPoseNativeError
+    dev = torch.device(DEV)
+    model = bench.build_models(dev)
+    model.bank_cache_dir = str(tmp_path)
+    templates = bench.SyntheticTemplates(2, 8, dev)
+    model.template_datasets = {"synthetic": templates}
+    model.test_dataset_name = "synthetic"
+    batch, labels, views = bench.make_queries(templates, 4, seed=2)
+    first = model.retrieve(batch, "synthetic")
+    files = [f for f in os.listdir(tmp_path) if f.endswith(".gpbank")]
+    assert len(files) == 1
+    path = os.path.join(tmp_path, files[0])
+    eng = model.engines["synthetic"]
+    assert os.path.getsize(path) > eng.bank_bytes
+    # second model instance: the cache is hit (the template encoders never run) and the results are identical
+    model2 = bench.build_models(dev)
+    model2.bank_cache_dir = str(tmp_path)
+    model2.template_datasets = {"synthetic": templates}
+    model2.test_dataset_name = "synthetic"
+    calls = {"n": 0}
+    orig = model2.ae_net.patch_tokens
+    model2.ae_net.patch_tokens = lambda x: (calls.__setitem__("n", calls["n"] + x.shape[0]), orig(x))[1]
+    second = model2.retrieve(batch, "synthetic")
+    assert calls["n"] == 4                                  # only the 4 query crops went through the ViT
+    for name in ("id_src", "pred_poses", "scores"):
+        assert torch.equal(getattr(first, name).cpu(), getattr(second, name).cpu()), name
+    # a bank of another shape refuses the file
+    other = Engine(2, 9, 8, device=DEV)
+    with pytest.raises(GigaPoseNativeError, match="does not match"):
+        other.load_bank(path)
