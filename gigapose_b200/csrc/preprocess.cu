@@ -5,9 +5,10 @@
 // mean/std normalisation, configs/data/transform.yaml:2-7).  The reference does this per detection in a python loop on
 // the CPU; here one thread produces one output pixel (all channels) by composing the index maps -- a pure gather.
 //
-// Index arithmetic follows ATen's nearest kernels for outputs larger than 128 (the only ones reachable at
-// target >= 128): out = floor(in * scale) in double, src = min(floorf(dst * float(1 / scale)), in - 1) for the first
-// resize, src = min(floorf(dst * (float(in) / out)), in - 1) for the second.
+// Index arithmetic follows ATen's CPU nearest kernels: out = floor(in * scale) in double, src = min(floorf(dst *
+// float(1 / scale)), in - 1) for the first resize (with the identity / dst >> 1 special cases of the small-output kernel
+// when out_h + out_w <= 128), src = min(floorf(dst * (float(in) / out)), in - 1) for the second, whose output
+// (2 * target > 128) always takes the plain path.
 #include "../../include/gigapose_b200.h"
 #include "gigapose_kernels.h"
 
@@ -83,9 +84,17 @@ crop_resize_pad_kernel(int C, int H, int W, int T, const float* __restrict__ ima
   const bool inside = pr >= 0 && pr < g.rh && pc >= 0 && pc < g.rw;
   size_t src = 0;
   if (inside) {
-    const int sr = g.y1 + min((int)floorf((float)pr * g.inv1), g.ch - 1);
-    const int sc = g.x1 + min((int)floorf((float)pc * g.inv1), g.cw - 1);
-    src = (size_t)sr * W + sc;
+    // ATen routes outputs with out_h + out_w <= 128 (a heavily clipped box) to a kernel whose index function keeps an
+    // unchanged size as the identity and an exactly doubled size as dst >> 1 instead of the float arithmetic
+    const bool small = g.rh + g.rw <= 128;
+    int lr, lc;
+    if (small && g.rh == g.ch) lr = pr;
+    else if (small && g.rh == 2 * g.ch) lr = pr >> 1;
+    else lr = min((int)floorf((float)pr * g.inv1), g.ch - 1);
+    if (small && g.rw == g.cw) lc = pc;
+    else if (small && g.rw == 2 * g.cw) lc = pc >> 1;
+    else lc = min((int)floorf((float)pc * g.inv1), g.cw - 1);
+    src = (size_t)(g.y1 + lr) * W + (g.x1 + lc);
   }
   const size_t plane = (size_t)H * W;
   const size_t img = image_index ? (size_t)image_index[det] : (size_t)det;
