@@ -74,3 +74,42 @@ def test_generator_is_deterministic_and_planted():
     assert (sim[w[s_ok], s_ok] > 0.5).float().mean() > 0.95      # planted pairs are well above the 0.5 threshold
     ref = synth.to_reference_layout(a)
     assert ref["src_feats"].shape == (2, 6, 1024, 16, 16) and ref["src_masks"].shape == (2, 6, 224, 224)
+
+
+def test_ist_trunk_weight_folding_matches_eval_mode_modules():
+    """Host logic of the native IST trunk (row a6): BatchNorm folding + [cout,kh,kw,cin] filter layout in the execution
+    order `gp_ist_trunk_create` documents, checked on the CPU against the eval-mode torch modules."""
+    import torch
+    import torch.nn.functional as F
+    from gigapose_b200 import ist_trunk
+    from src.models.network.resnet import ResNet
+    torch.manual_seed(3)
+    net = ResNet(dict(n_heads=0, input_dim=3, input_size=256, initial_dim=128, block_dims=[128, 192, 256, 512],
+                      descriptor_size=256)).eval()
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.2); m.running_var.uniform_(0.5, 1.5); m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.2)
+    assert ist_trunk.supports(net) and net.backend == "native"
+    convs = ist_trunk.folded_convs_in_abi_order(net, "cpu")
+    assert len(convs) == ist_trunk.NUM_CONVS == 21
+    shapes = [tuple(w.shape) for w, _ in convs]
+    assert shapes[0] == (128, 7, 7, 3) and shapes[-1] == (256, 1, 1, 512) and convs[-1][1] is None
+    assert shapes[5] == (192, 3, 3, 128) and shapes[6] == (192, 1, 1, 128) and shapes[7] == (192, 3, 3, 192)   # conv1, downsample, conv2
+
+    def conv(x, wb, stride, pad):
+        w, b = wb
+        return F.conv2d(x, w.permute(0, 3, 1, 2), b, stride=stride, padding=pad)
+
+    with torch.no_grad():
+        x = torch.randn(1, 3, 64, 64)
+        assert torch.allclose(conv(x, convs[0], 2, 3), net.bn1(net.conv1(x)), atol=1e-5)
+        t = torch.randn(1, 128, 16, 16)
+        blk = net.layer2[0]                                                # the first strided block: entries 5, 6, 7
+        y = F.relu(conv(t, convs[5], 2, 1))
+        want = F.relu(blk.downsample(t) + blk.bn2(blk.conv2(F.relu(blk.bn1(blk.conv1(t))))))
+        got = F.relu(conv(t, convs[6], 2, 0) + conv(y, convs[7], 1, 1))
+        assert torch.allclose(got, want, atol=1e-4)
+    other = ResNet(dict(n_heads=0, input_dim=3, input_size=256, initial_dim=64, block_dims=[64, 128, 256, 512],
+                        descriptor_size=256))
+    assert not ist_trunk.supports(other)                                   # other geometries stay on the torch path
