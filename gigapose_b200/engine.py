@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Dict, Optional, Sequence
+from typing import Dict, Optional
 
 import torch
 

@@ -174,7 +174,6 @@ class ShardedRetriever:
 def run_sharded_bench(args, cfg, config, wl_name, rank, world, device, METRIC, UNIT, ClockSampler, emit):
     """bench.py body for N > 1 (launched by torch.distributed.run, one rank per GPU)."""
     import bench
-    from . import vit_engine
     ist_backend = getattr(args, "ist_backend", "native")
     model = bench.build_models(device, ist_backend=ist_backend)
     templates = bench.SyntheticTemplates(cfg["O"], cfg["T"], device)

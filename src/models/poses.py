@@ -1,6 +1,5 @@
 """`ObjectPoseRecovery` -- drop-in for `src/models/poses.py:12-163`: RANSAC over the k hypotheses and lifting of
 (template id, 2-D similarity, crop matrices, intrinsics) to a 6-D pose, in gigapose_b200/csrc/ransac_pose.cu."""
-import ctypes as C
 
 import torch
 
