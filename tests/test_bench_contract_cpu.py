@@ -1,0 +1,35 @@
+"""bench.py contract on the CPU: the reference arm (`--impl reference`, the one leg that runs without a GPU) prints
+exactly one JSON line on stdout with the keys the driver reads; `rows_config` names every §8 row."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--workload", "c1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "detections/s" and d["higher_is_better"] is True
+    for key in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data",
+                "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["value"] > 0 and d["e2e"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_rows_config_lists_every_native_row():
+    sys.path.insert(0, ROOT)
+    import bench
+    native = bench.rows_config("native")
+    assert native["library_rows"] == [] and len(native["native_rows"]) == 9
+    assert any(r.startswith("a6") for r in native["native_rows"])
+    cudnn = bench.rows_config("cudnn")
+    assert len(cudnn["library_rows"]) == 1 and not any(r.startswith("a6") for r in cudnn["native_rows"])

@@ -38,3 +38,27 @@ def test_known_answer_wide_box_is_centred_with_zero_rows():
     rows = out["images"][0, 0].sum(1)
     assert int((rows > 0).sum()) == 32 and bool((rows[:48] == 0).all()) and bool((rows[80:] == 0).all())
     assert out["M"][0, 1, 2].item() == 48 - 2 * 10 and out["M"][0, 0, 2].item() == -2 * 10
+
+
+def test_M_maps_sampled_source_pixels_onto_their_output_pixels():
+    """Size-independent property (any image / box): the matrix M returned with a crop sends the source pixel an output
+    pixel was copied from back to within one output pixel of it (nearest sampling: < scale + 1), at the shipped size."""
+    g = torch.Generator().manual_seed(5)
+    H, W, T, n = 240, 320, 224, 12
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    coords = torch.stack([xx, yy]).unsqueeze(0).expand(n, 2, H, W) + 1.0          # +1: zero stays "padding"
+    x1 = torch.randint(0, W - 40, (n,), generator=g); y1 = torch.randint(0, H - 40, (n,), generator=g)
+    x2 = (x1 + torch.randint(20, 200, (n,), generator=g)).clamp(max=W); y2 = (y1 + torch.randint(20, 200, (n,), generator=g)).clamp(max=H)
+    boxes = torch.stack([x1, y1, x2, y2], -1)
+    out = port.crop_resize_pad(boxes, coords, target_size=T)
+    oy, ox = torch.meshgrid(torch.arange(T, dtype=torch.float32), torch.arange(T, dtype=torch.float32), indexing="ij")
+    for i in range(n):
+        sx, sy = out["images"][i, 0] - 1.0, out["images"][i, 1] - 1.0             # source coordinates of every output pixel
+        inside = out["images"][i, 0] > 0
+        assert inside.any()
+        M = out["M"][i]
+        px = M[0, 0] * sx + M[0, 2]
+        py = M[1, 1] * sy + M[1, 2]
+        scale = M[0, 0].item()
+        assert ((px - ox)[inside].abs() < scale + 1).all() and ((py - oy)[inside].abs() < scale + 1).all()
+        assert ((px - ox)[inside] <= 1e-3).all() and ((py - oy)[inside] <= 1e-3).all()   # floor sampling never overshoots
