@@ -48,6 +48,8 @@ WORKLOADS = {
     "c3": dict(O=30, T=162, B=64, desc="T-LESS-shaped: 30 objects x 162 templates, batch 64"),
     "c4": dict(O=21, T=162, B=128, desc="YCB-V-shaped: 21 objects x 162 templates, batch 128"),
 }
+DTYPE = ("f32 (a1, a4, a6: bf16 hi/lo split x3 on tensor cores with fp32 accumulate = fp32-faithful; "
+         "a5, a7-a9: fp32)")
 METRIC = "detections/sec (224x224 crops, 162-template bank)"
 UNIT = "detections/s"
 
@@ -55,16 +57,14 @@ UNIT = "detections/s"
 # ----------------------------------------------------------------------------------------------------------------
 # synthetic world: template crops per object, queries = noisy copies of planted templates
 # ----------------------------------------------------------------------------------------------------------------
-def rows_config(ist_backend):
-    """Which SURVEY §8 rows run on this library's kernels and which on a vendor library."""
+def rows_config():
+    """Which SURVEY §8 rows run on this library's kernels (all of them) and which on a vendor library (none)."""
     from gigapose_b200 import vit_engine, ist_trunk
-    native = [f"a1 ViT-L/14 ({vit_engine.BACKEND})", "a2", "a3", "a4", "a5", "a7", "a8", "a9"]
-    if ist_backend == "native":
-        return dict(native_rows=native[:5] + [f"a6 IST ResNet ({ist_trunk.BACKEND})"] + native[5:], library_rows=[])
-    return dict(native_rows=native, library_rows=["a6 IST ResNet (cuDNN TF32 via torch, selected with --ist-backend cudnn)"])
+    return dict(native_rows=[f"a1 ViT-L/14 ({vit_engine.BACKEND})", "a2", "a3", "a4", "a5",
+                             f"a6 IST ResNet ({ist_trunk.BACKEND})", "a7", "a8", "a9"], library_rows=[])
 
 
-def build_models(device, seed_vit=7, seed_ist=8, ist_backend="native"):
+def build_models(device, seed_vit=7, seed_ist=8):
     from gigapose_b200.vit import DinoVisionTransformer
     from src.models.gigaPose import GigaPose
     from src.models.matching import LocalSimilarity
@@ -76,7 +76,7 @@ def build_models(device, seed_vit=7, seed_ist=8, ist_backend="native"):
     ae = AENet("dinov2_vitl14", dinov2_model=vit, descriptor_size=1024, max_batch_size=64)
     torch.manual_seed(seed_ist)
     backbone = ResNet(dict(n_heads=0, input_dim=3, input_size=256, initial_dim=128, block_dims=[128, 192, 256, 512],
-                           descriptor_size=256, backend=ist_backend))
+                           descriptor_size=256))
     reg = Regressor(descriptor_size=256, hidden_dim=256, use_tanh_act=True, normalize_output=True)
     ist = ISTNet("resnet", backbone, reg, max_batch_size=64)
     g = torch.Generator().manual_seed(seed_ist + 1)
@@ -311,8 +311,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ist-backend", default="native", choices=["native", "cudnn"],
-                    help="IST trunk (row a6): native tcgen05 implicit-GEMM kernels (default) or the cuDNN/TF32 library path")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch the per-batch kernel sequence eagerly")
     ap.add_argument("--profile-range", action="store_true",
                     help="wrap ONE extra resident step in cudaProfilerStart/Stop (ncu --profile-from-start off)")
@@ -363,7 +361,7 @@ def main():
         return run_sharded_bench(args, cfg, config, wl_name, rank, world, device, METRIC, UNIT, ClockSampler, emit)
 
     from gigapose_b200 import vit_engine
-    model = build_models(device, ist_backend=args.ist_backend)
+    model = build_models(device)
     model.use_cuda_graph = not args.no_cuda_graph and not args.profile_range
     templates = SyntheticTemplates(cfg["O"], cfg["T"], device)
     model.template_datasets = {"synthetic": templates}
@@ -441,9 +439,11 @@ def main():
     h2d = sum(batch_host._tensors[k].numel() * batch_host._tensors[k].element_size() for k in ("tar_img", "tar_mask", "tar_K", "tar_M"))
     d2h = poses.numel() * 4 + scores.numel() * 4
 
-    # sanity: planted view recovered (counts, not asserted: weights are random-init)
+    # correctness gate of the measured step: every query is a noisy copy of template `views[b]` of its object, and that
+    # view must be among the k retrieved (a bench line for a path that retrieves the wrong templates is worthless)
     id0 = pred.id_src.cpu()
     hit = float((id0 == views[:, None]).any(dim=1).float().mean())
+    assert hit == 1.0, f"planted view missing from the top-k of {1 - hit:.1%} of the queries"
 
     # roofline of the dominant kernel (similarity search): algorithmic FLOPs / CUDA-event time of the kernel alone
     peaks = {}
@@ -472,9 +472,8 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (a1, a4: bf16 hi/lo split x3 on tensor cores with fp32 accumulate = fp32-faithful; a5, a7-a9: fp32; "
-                     + ("a6: same split on the implicit-GEMM convolutions)" if args.ist_backend == "native" else "a6: TF32 cuDNN)"),
-            "data": "synthetic", "config": dict(config, **rows_config(args.ist_backend),
+            "dtype": DTYPE,
+            "data": "synthetic", "config": dict(config, **rows_config(),
                                                 planted_view_in_topk=hit),
             "clocks": clocks.summary(),
             "e2e": {"value": cfg["B"] / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgigapose_b200.so")
 
-GP_ABI_VERSION = 1
+GP_ABI_VERSION = 2
 LAYOUT_CHANNEL_MAJOR = 0
 LAYOUT_PATCH_MAJOR = 1
 PRECISION_FP32_SPLIT = 0
@@ -24,6 +24,7 @@ class GpConfig(C.Structure):
         ("num_templates_global", C.c_int32), ("template_id_stride", C.c_int32), ("template_id_offset", C.c_int32),
         ("max_batch", C.c_int32), ("top_k", C.c_int32), ("sim_threshold", C.c_float), ("patch_threshold", C.c_float),
         ("pixel_threshold", C.c_float), ("patch_size", C.c_int32), ("precision", C.c_int32),
+        ("ist_bank_global", C.c_int32),
     ]
 
 
@@ -56,6 +57,7 @@ SYMBOLS = {
     "gp_destroy": (C.c_int, [C.c_void_p]),
     "gp_bank_write": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                 C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "gp_bank_write_ist": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "gp_bank_set_poses": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gp_set_ist_weights": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int]),
     "gp_set_queries": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
@@ -64,13 +66,18 @@ SYMBOLS = {
     "gp_topk_merge": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(GpCandidates), C.c_size_t, C.POINTER(GpMatches),
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "gp_sim_topk": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GpMatches), C.c_void_p]),
-    "gp_ist_mlp": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(GpMatches), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gp_ist_mlp": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(GpMatches), C.c_void_p, C.c_void_p,
+                             C.c_void_p]),
     "gp_ransac": (C.c_int, [C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                             C.POINTER(GpRansacOut), C.c_void_p]),
     "gp_pose_recover": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "gp_sort_and_pose": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(GpMatches), C.c_void_p,
-                                   C.c_void_p, C.POINTER(GpRansacOut), C.POINTER(GpPredictions), C.c_void_p]),
+    "gp_sort_and_pose": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(GpMatches),
+                                   C.c_void_p, C.c_void_p, C.POINTER(GpRansacOut), C.POINTER(GpPredictions), C.c_void_p]),
+    "gp_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "gp_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gp_topk_allgather_merge": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(GpCandidates),
+                                          C.POINTER(GpMatches), C.c_void_p]),
     "gp_vit_query_sizes": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "gp_vit_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -5,6 +5,7 @@
 #include "gigapose_kernels.h"
 
 #include <atomic>
+#include <dlfcn.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -171,7 +172,7 @@ void carve_bank(Carver& c, const gp_config_t& cfg, Bank* b) {
   tmp.hi = c.take<uint16_t>(OT * GP_NUM_PATCHES * GP_AE_DIM);
   tmp.lo = c.take<uint16_t>(OT * GP_NUM_PATCHES * GP_AE_DIM);
   tmp.mask16 = c.take<float>(OT * GP_NUM_PATCHES);
-  tmp.ist = c.take<float>(OT * GP_NUM_PATCHES * GP_IST_DIM);
+  tmp.ist = c.take<float>((cfg.ist_bank_global ? OTg : OT) * GP_NUM_PATCHES * GP_IST_DIM);
   tmp.K = c.take<float>((size_t)cfg.num_objects * 9);
   tmp.M = c.take<float>(OTg * 9);
   tmp.pose = c.take<float>(OTg * 16);
@@ -215,6 +216,7 @@ int validate(const gp_config_t* cfg) {
   if (cfg->patch_size < 1) return fail(GP_ERR_INVALID, "patch_size must be >= 1");
   if (cfg->precision != GP_PRECISION_FP32_SPLIT && cfg->precision != GP_PRECISION_BF16)
     return fail(GP_ERR_INVALID, "unknown precision %d", cfg->precision);
+  if (cfg->ist_bank_global != 0 && cfg->ist_bank_global != 1) return fail(GP_ERR_INVALID, "ist_bank_global must be 0 or 1");
   if ((size_t)cfg->num_objects * cfg->num_templates * GP_NUM_PATCHES * 32 >= (1ull << 31))
     return fail(GP_ERR_INVALID, "bank has too many rows for 32-bit TMA coordinates");
   return GP_OK;
@@ -231,7 +233,33 @@ struct gp_context {
   gp::IstMlpWeights mlp;
   bool mlp_set;
   int cur_B;      // batch size staged by gp_set_queries (0 = none)
+  void* nccl_comm;   // ncclComm_t bound by gp_comm_init (not owned)
+  int rank, world;
 };
+
+namespace {
+// ncclAllGather(sendbuff, recvbuff, sendcount, datatype, comm, stream), resolved from the libnccl the host process has
+// already loaded (torch's bundled libnccl.so.2): the library itself carries no link-time NCCL dependency
+typedef int (*NcclAllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef const char* (*NcclErrFn)(int);
+NcclAllGatherFn g_allgather = nullptr;
+NcclErrFn g_nccl_err = nullptr;
+int resolve_nccl() {
+  if (g_allgather) return GP_OK;
+  void* sym = dlsym(RTLD_DEFAULT, "ncclAllGather");
+  void* lib = nullptr;
+  if (!sym) {
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (lib) sym = dlsym(lib, "ncclAllGather");
+  }
+  if (!sym) return fail(GP_ERR_UNSUPPORTED, "ncclAllGather not found: load libnccl.so.2 (e.g. import torch) before gp_comm_init");
+  g_allgather = reinterpret_cast<NcclAllGatherFn>(sym);
+  void* es = dlsym(RTLD_DEFAULT, "ncclGetErrorString");
+  if (!es && lib) es = dlsym(lib, "ncclGetErrorString");
+  g_nccl_err = reinterpret_cast<NcclErrFn>(es);
+  return GP_OK;
+}
+}  // namespace
 
 extern "C" {
 
@@ -269,6 +297,9 @@ int gp_create(const gp_config_t* cfg, void* bank_mem, void* workspace_mem, gp_ha
   h->num_sms = prop.multiProcessorCount;
   h->mlp_set = false;
   h->cur_B = 0;
+  h->nccl_comm = nullptr;
+  h->rank = 0;
+  h->world = 1;
   Carver cb(bank_mem), cw(workspace_mem);
   carve_bank(cb, *cfg, &h->bank);
   carve_workspace(cw, *cfg, &h->ws);
@@ -315,8 +346,29 @@ int gp_bank_write(gp_handle_t h, int obj, int tmpl0, int n, const float* feat, i
   GP_CUDA(gp::launch_sample_mask16(mask, n, H, W, h->bank.mask16 + slot * GP_NUM_PATCHES, s));
   g_launches += 2;
   if (ist_feat) {
+    if (c.ist_bank_global) return fail(GP_ERR_INVALID, "cfg.ist_bank_global = 1: write IST features with gp_bank_write_ist (global ids)");
     GP_CUDA(gp::launch_transpose_cp(ist_feat, n, GP_IST_DIM, h->bank.ist + slot * GP_NUM_PATCHES * GP_IST_DIM, s));
     g_launches += 1;
+  }
+  return GP_OK;
+}
+
+int gp_bank_write_ist(gp_handle_t h, int obj, int tmpl0, int n, const float* ist_feat, int ist_layout, void* stream) {
+  if (!h || !ist_feat) return fail(GP_ERR_INVALID, "null argument");
+  const gp_config_t& c = h->cfg;
+  const int Ti = c.ist_bank_global ? c.num_templates_global : c.num_templates;
+  if (obj < 0 || obj >= c.num_objects || tmpl0 < 0 || n < 1 || tmpl0 + n > Ti)
+    return fail(GP_ERR_INVALID, "IST template range [%d,%d) of object %d outside the bank (%d x %d)", tmpl0, tmpl0 + n, obj,
+                c.num_objects, Ti);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* dst = h->bank.ist + ((size_t)obj * Ti + tmpl0) * GP_NUM_PATCHES * GP_IST_DIM;
+  if (ist_layout == GP_LAYOUT_CHANNEL_MAJOR) {
+    GP_CUDA(gp::launch_transpose_cp(ist_feat, n, GP_IST_DIM, dst, s));
+    g_launches += 1;
+  } else if (ist_layout == GP_LAYOUT_PATCH_MAJOR) {
+    GP_CUDA(cudaMemcpyAsync(dst, ist_feat, (size_t)n * GP_NUM_PATCHES * GP_IST_DIM * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  } else {
+    return fail(GP_ERR_INVALID, "unknown IST feature layout %d", ist_layout);
   }
   return GP_OK;
 }
@@ -362,8 +414,9 @@ int gp_set_queries(gp_handle_t h, int B, const float* q_feat, int feat_layout, i
   else
     return fail(GP_ERR_INVALID, "unknown feature layout %d", feat_layout);
   GP_CUDA(gp::launch_sample_mask16(q_mask, B, H, W, h->ws.q_mask16, s));
-  GP_CUDA(cudaMemcpyAsync(h->ws.q_obj, q_obj, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, s));
-  GP_CUDA(gp::launch_object_order(h->ws.q_obj, B, h->cfg.num_objects, h->ws.perm, s));
+  // object ids are clamped into [0, O) on the way in: an out-of-range label must not turn into an out-of-bounds bank
+  // address (the host-side callers validate and raise; see GigaPose.retrieve)
+  GP_CUDA(gp::launch_object_order(q_obj, B, h->cfg.num_objects, h->ws.q_obj, h->ws.perm, s));
   g_launches += 3;
   h->cur_B = B;
   return GP_OK;
@@ -432,24 +485,34 @@ int gp_sim_topk(gp_handle_t h, int B, const gp_matches_t* out, void* stream) {
   return gp_topk_merge(h, B, 1, &c, 0, out, nullptr, nullptr, stream);
 }
 
-int gp_ist_mlp(gp_handle_t h, int B, const float* q_ist, const gp_matches_t* m, float* rel_scale, float* rel_inplane,
-               void* stream) {
+int gp_ist_mlp(gp_handle_t h, int b0, int n, const float* q_ist, int ist_layout, const gp_matches_t* m, float* rel_scale,
+               float* rel_inplane, void* stream) {
   if (!h || !q_ist || !m || !rel_scale || !rel_inplane) return fail(GP_ERR_INVALID, "null argument");
   if (!h->mlp_set) return fail(GP_ERR_STATE, "gp_set_ist_weights has not been called");
-  if (B != h->cur_B) return fail(GP_ERR_STATE, "gp_set_queries staged %d queries, gp_ist_mlp asked for %d", h->cur_B, B);
+  if (b0 < 0 || n < 1 || b0 + n > h->cur_B)
+    return fail(GP_ERR_STATE, "gp_set_queries staged %d queries, gp_ist_mlp asked for [%d,%d)", h->cur_B, b0, b0 + n);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  GP_CUDA(gp::launch_transpose_cp(q_ist, B, GP_IST_DIM, h->ws.q_ist, s));
+  const float* q_pm = q_ist;
+  if (ist_layout == GP_LAYOUT_CHANNEL_MAJOR) {
+    GP_CUDA(gp::launch_transpose_cp(q_ist, n, GP_IST_DIM, h->ws.q_ist, s));
+    q_pm = h->ws.q_ist;
+    g_launches += 1;
+  } else if (ist_layout != GP_LAYOUT_PATCH_MAJOR) {
+    return fail(GP_ERR_INVALID, "unknown IST feature layout %d", ist_layout);
+  }
+  const gp_config_t& c = h->cfg;
   gp::IstMlpParams p;
-  p.B = B; p.k = h->cfg.top_k; p.T = h->cfg.num_templates;
-  p.id_stride = h->cfg.template_id_stride; p.id_offset = h->cfg.template_id_offset;
+  p.B = n; p.k = c.top_k;
+  if (c.ist_bank_global) { p.T = c.num_templates_global; p.id_stride = 1; p.id_offset = 0; }
+  else { p.T = c.num_templates; p.id_stride = c.template_id_stride; p.id_offset = c.template_id_offset; }
   p.id_src = reinterpret_cast<const long long*>(m->id_src);
   p.src_pts = reinterpret_cast<const long long*>(m->src_pts);
   p.tar_pts = reinterpret_cast<const long long*>(m->tar_pts);
-  p.q_obj = h->ws.q_obj; p.q_ist = h->ws.q_ist; p.bank_ist = h->bank.ist;
+  p.q_obj = h->ws.q_obj + b0; p.q_ist = q_pm; p.bank_ist = h->bank.ist;
   p.rel_scale = rel_scale; p.rel_inplane = rel_inplane;
   p.row_count = h->ws.row_count; p.row_ids = h->ws.row_ids; p.hidden1 = h->ws.hidden1; p.hidden2 = h->ws.hidden2;
   GP_CUDA(gp::launch_ist_mlp(h->mlp, p, s));
-  g_launches += 5;
+  g_launches += 4;
   return GP_OK;
 }
 
@@ -486,14 +549,16 @@ int gp_pose_recover(int B, int k, int num_templates, const int32_t* q_obj, const
   return GP_OK;
 }
 
-int gp_sort_and_pose(gp_handle_t h, int B, const float* q_K, const float* q_M, const gp_matches_t* m,
-                     const float* rel_scale, const float* rel_inplane, const gp_ransac_out_t* r,
+int gp_sort_and_pose(gp_handle_t h, int b0, int n, int sort_by_inliers, const float* q_K, const float* q_M,
+                     const gp_matches_t* m, const float* rel_scale, const float* rel_inplane, const gp_ransac_out_t* r,
                      const gp_predictions_t* o, void* stream) {
   if (!h || !q_K || !q_M || !m || !rel_scale || !rel_inplane || !r || !o) return fail(GP_ERR_INVALID, "null argument");
-  if (B != h->cur_B) return fail(GP_ERR_STATE, "gp_set_queries staged %d queries, gp_sort_and_pose asked for %d", h->cur_B, B);
+  if (b0 < 0 || n < 1 || b0 + n > h->cur_B)
+    return fail(GP_ERR_STATE, "gp_set_queries staged %d queries, gp_sort_and_pose asked for [%d,%d)", h->cur_B, b0, b0 + n);
   gp::PoseParams p;
-  p.B = B; p.k = h->cfg.top_k; p.T = h->cfg.num_templates_global;
-  p.q_obj = h->ws.q_obj; p.q_K = q_K; p.q_M = q_M;
+  p.B = n; p.k = h->cfg.top_k; p.T = h->cfg.num_templates_global;
+  p.sort = sort_by_inliers ? 1 : 0;
+  p.q_obj = h->ws.q_obj + b0; p.q_K = q_K; p.q_M = q_M;
   p.tmpl_K = h->bank.K; p.tmpl_M = h->bank.M; p.tmpl_pose = h->bank.pose;
   p.in_count = r->inlier_count;
   p.id_src = reinterpret_cast<const long long*>(m->id_src); p.score_src = m->score_src; p.score_pts = m->score_pts;
@@ -515,6 +580,38 @@ int gp_sort_and_pose(gp_handle_t h, int B, const float* q_K, const float* q_M, c
   GP_CUDA(gp::launch_sort_and_pose(p, static_cast<cudaStream_t>(stream)));
   g_launches += 1;
   return GP_OK;
+}
+
+int gp_comm_init(gp_handle_t h, void* nccl_comm, int rank, int world) {
+  if (!h || !nccl_comm) return fail(GP_ERR_INVALID, "null argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail(GP_ERR_INVALID, "rank %d outside [0, world=%d)", rank, world);
+  if (world != h->cfg.template_id_stride || rank != h->cfg.template_id_offset)
+    return fail(GP_ERR_INVALID, "communicator (rank %d of %d) does not match the shard map of this handle (offset %d, stride %d)",
+                rank, world, h->cfg.template_id_offset, h->cfg.template_id_stride);
+  if (world * h->cfg.top_k > 64) return fail(GP_ERR_INVALID, "world * top_k = %d exceeds the merge kernel's 64 candidates", world * h->cfg.top_k);
+  if (int e = resolve_nccl()) return e;
+  h->nccl_comm = nccl_comm;
+  h->rank = rank;
+  h->world = world;
+  return GP_OK;
+}
+
+int gp_allgather(gp_handle_t h, const void* send, void* recv, size_t bytes_per_rank, void* stream) {
+  if (!h || !send || !recv) return fail(GP_ERR_INVALID, "null argument");
+  if (!h->nccl_comm) return fail(GP_ERR_STATE, "gp_comm_init has not been called");
+  const int r = g_allgather(send, recv, bytes_per_rank, /*ncclInt8*/ 0, h->nccl_comm, static_cast<cudaStream_t>(stream));
+  if (r != 0) return fail(GP_ERR_CUDA, "ncclAllGather failed: %s", g_nccl_err ? g_nccl_err(r) : "?");
+  return GP_OK;
+}
+
+int gp_topk_allgather_merge(gp_handle_t h, int B, void* packed, size_t rank_stride_bytes, const gp_candidates_t* slot0,
+                            const gp_matches_t* out, void* stream) {
+  if (!h || !packed || !slot0 || !out) return fail(GP_ERR_INVALID, "null argument");
+  if (!h->nccl_comm) return fail(GP_ERR_STATE, "gp_comm_init has not been called");
+  if (B != h->cur_B) return fail(GP_ERR_STATE, "gp_set_queries staged %d queries, merge asked for %d", h->cur_B, B);
+  uint8_t* base = static_cast<uint8_t*>(packed);
+  if (int e = gp_allgather(h, base + (size_t)h->rank * rank_stride_bytes, base, rank_stride_bytes, stream)) return e;
+  return gp_topk_merge(h, B, h->world, slot0, rank_stride_bytes, out, nullptr, nullptr, stream);
 }
 
 int gp_debug_sim_tiles(gp_handle_t h, int B, float* tiles, void* stream) {

@@ -75,7 +75,7 @@ cudaError_t launch_split_descriptors(const float* x, long long n_rows, int C, in
 // nearest-neighbour H x W -> 16 x 16 sampling of float masks (F.interpolate default mode), [n,H,W] -> [n,256]
 cudaError_t launch_sample_mask16(const float* mask, long long n, int H, int W, float* out, cudaStream_t stream);
 // perm[B] = stable order of the queries by object id, so that tiles sharing a template run back to back
-cudaError_t launch_object_order(const int* q_obj, int B, int num_objects, int* perm, cudaStream_t stream);
+cudaError_t launch_object_order(const int* q_obj, int B, int num_objects, int* q_obj_out, int* perm, cudaStream_t stream);
 // [n, C, 256] (channel-major, reference layout) -> [n, 256, C] (patch-major)
 cudaError_t launch_transpose_cp(const float* in, long long n, int C, float* out, cudaStream_t stream);
 
@@ -125,6 +125,7 @@ cudaError_t launch_ransac(const RansacParams& p, cudaStream_t stream);
 
 struct PoseParams {
   int B, k, T;                // T = GLOBAL templates per object in the pose tables
+  int sort;                   // 1: stable re-sort by inlier count (gigaPose.py:590-595); 0: keep the retrieval order
   const int* q_obj;           // [B]
   const float* q_K;           // [B,3,3]
   const float* q_M;           // [B,3,3]

@@ -98,24 +98,26 @@ __global__ void transpose_cp_kernel(const float* __restrict__ in, int C, float* 
 }
 
 // perm = stable order of the queries by object id (rank by counting; B is at most a few hundred)
-__global__ void object_order_kernel(const int* __restrict__ q_obj, int B, int* __restrict__ perm) {
+// also writes the clamped copy of the object ids the other kernels index the bank with
+__global__ void object_order_kernel(const int* __restrict__ q_obj, int B, int num_objects, int* __restrict__ q_obj_out,
+                                    int* __restrict__ perm) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
-    const int mine = q_obj[i];
+    const int mine = min(max(q_obj[i], 0), num_objects - 1);
     int rank = 0;
     for (int j = 0; j < B; ++j) {
-      const int o = q_obj[j];
+      const int o = min(max(q_obj[j], 0), num_objects - 1);
       rank += (o < mine || (o == mine && j < i)) ? 1 : 0;
     }
     perm[rank] = i;
+    q_obj_out[i] = mine;
   }
 }
 
 }  // namespace
 
-cudaError_t launch_object_order(const int* q_obj, int B, int num_objects, int* perm, cudaStream_t stream) {
-  (void)num_objects;
+cudaError_t launch_object_order(const int* q_obj, int B, int num_objects, int* q_obj_out, int* perm, cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
-  object_order_kernel<<<(B + 127) / 128, 128, 0, stream>>>(q_obj, B, perm);
+  object_order_kernel<<<(B + 127) / 128, 128, 0, stream>>>(q_obj, B, num_objects, q_obj_out, perm);
   return cudaGetLastError();
 }
 

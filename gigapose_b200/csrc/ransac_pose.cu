@@ -207,7 +207,7 @@ sort_and_pose_kernel(PoseParams p) {
     // stable insertion sort, descending by inlier count (== descending score)
     int cnt[32];
     for (int i = 0; i < k; ++i) { cnt[i] = p.in_count[(size_t)b * k + i]; s_order[i] = i; }
-    for (int i = 1; i < k; ++i) {
+    for (int i = 1; i < k && p.sort; ++i) {
       const int oi = s_order[i], ci = cnt[oi];
       int j = i - 1;
       while (j >= 0 && cnt[s_order[j]] < ci) { s_order[j + 1] = s_order[j]; --j; }

@@ -43,6 +43,16 @@ def _feature_layout(feat: torch.Tensor):
     return feat.contiguous(), LAYOUT_PATCH_MAJOR
 
 
+def _ist_layout(feat: torch.Tensor):
+    """[n,256,16,16] IST features; the channels-last view the native trunk returns ([n,16,16,256] memory) is taken in
+    place as patch-major, anything else is made contiguous channel-major."""
+    n, c, h, w = feat.shape
+    assert (c, h * w) == (C_IST, P), tuple(feat.shape)
+    if feat.stride() == (P * c, 1, w * c, c):
+        return feat, LAYOUT_PATCH_MAJOR
+    return feat.contiguous(), LAYOUT_CHANNEL_MAJOR
+
+
 def ransac_points(lib, src_pts, tar_pts, rel_scale, rel_inplane, out, pixel_threshold, patch_size, stream):
     """gp_ransac over n = prod(leading dims) (detection, hypothesis) pairs; tensors [..., 256, 2] / [..., 256]."""
     n = src_pts.numel() // (P * 2)
@@ -57,7 +67,7 @@ class Engine:
     def __init__(self, num_objects: int, num_templates: int, max_batch: int, device="cuda:0", k: int = 5,
                  sim_threshold: float = 0.5, patch_threshold: float = 3, pixel_threshold: float = 14.0,
                  patch_size: int = 14, precision: str = "fp32_split", shard_rank: int = 0, shard_world: int = 1,
-                 num_templates_global: Optional[int] = None):
+                 num_templates_global: Optional[int] = None, ist_bank_global: bool = False):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -74,7 +84,9 @@ class Engine:
                        max_batch=self.max_batch, top_k=self.k, sim_threshold=float(sim_threshold),
                        patch_threshold=float(patch_threshold), pixel_threshold=float(pixel_threshold),
                        patch_size=int(patch_size),
-                       precision={"fp32_split": PRECISION_FP32_SPLIT, "bf16": PRECISION_BF16}[precision])
+                       precision={"fp32_split": PRECISION_FP32_SPLIT, "bf16": PRECISION_BF16}[precision],
+                       ist_bank_global=1 if ist_bank_global else 0)
+        self.ist_bank_global = bool(ist_bank_global)
         self.cfg = cfg
         self.precision = precision
         bank_b, ws_b = C.c_size_t(), C.c_size_t()
@@ -117,11 +129,19 @@ class Engine:
         mask = _f32(mask, self.device).contiguous()
         n = feat.shape[0]
         assert mask.shape[0] == n and mask.dim() == 3
-        if ist_feat is not None:
-            ist_feat = _f32(ist_feat, self.device).contiguous()
-            assert ist_feat.shape == (n, C_IST, 16, 16), tuple(ist_feat.shape)
         check(self.lib.gp_bank_write(self._h, obj, tmpl0, n, feat.data_ptr(), layout, norm_passes, mask.data_ptr(),
-                                     mask.shape[1], mask.shape[2], _ptr(ist_feat), self.stream))
+                                     mask.shape[1], mask.shape[2], None, self.stream))
+        if ist_feat is not None:
+            assert ist_feat.shape[0] == n
+            if self.ist_bank_global:
+                raise _lib.GigaPoseNativeError("ist_bank_global engine: write IST features with bank_write_ist(global ids)")
+            self.bank_write_ist(obj, tmpl0, ist_feat)
+
+    def bank_write_ist(self, obj: int, tmpl0: int, ist_feat: torch.Tensor) -> None:
+        """IST features [n,256,16,16] into IST-bank slots [tmpl0, tmpl0+n) of object `obj` (GLOBAL template ids when
+        the engine was created with `ist_bank_global=True`)."""
+        ist_feat, layout = _ist_layout(_f32(ist_feat, self.device))
+        check(self.lib.gp_bank_write_ist(self._h, obj, tmpl0, ist_feat.shape[0], ist_feat.data_ptr(), layout, self.stream))
 
     def set_poses(self, K: torch.Tensor, M: torch.Tensor, poses: torch.Tensor) -> None:
         K, M, poses = (_f32(x, self.device).contiguous() for x in (K, M, poses))
@@ -142,7 +162,8 @@ class Engine:
         return dict(format=self.BANK_FORMAT, abi_version=int(c.abi_version), num_objects=self.O, num_templates=self.T,
                     num_templates_global=self.T_global, template_id_stride=self.shard_world,
                     template_id_offset=self.shard_rank, precision=self.precision, patch_size=int(c.patch_size),
-                    bank_bytes=int(self.bank_bytes))
+                    ist_bank_global=int(self.ist_bank_global), bank_bytes=int(self.bank_bytes),
+                    fingerprint=getattr(self, "fingerprint", ""))
 
     def save_bank(self, path: str) -> None:
         """Writes the onboarded bank -- descriptor planes, sampled masks, IST features and pose tables exactly as they
@@ -182,8 +203,10 @@ class Engine:
         ws = []
         for head in (regressor.scale_predictor, regressor.inplane_predictor):
             for idx in (0, 2, 4):
-                ws.append(_f32(head[idx].weight.detach(), self.device).contiguous())
-                ws.append(_f32(head[idx].bias.detach(), self.device).contiguous())
+                # engine-owned copies (3 MB): the library retains raw pointers, which must not alias module parameters
+                # that a later `.to()` / `.half()` / load_state_dict could free or rewrite
+                ws.append(_f32(head[idx].weight.detach(), self.device).clone(memory_format=torch.contiguous_format))
+                ws.append(_f32(head[idx].bias.detach(), self.device).clone(memory_format=torch.contiguous_format))
         assert ws[0].shape == (512, 512) and ws[2].shape == (256, 512) and ws[4].shape == (1, 256)
         assert ws[6].shape == (512, 512) and ws[8].shape == (256, 512) and ws[10].shape == (2, 256)
         self._keep = ws
@@ -251,14 +274,16 @@ class Engine:
                                      self.stream))
         return (m, rs, ri) if rs is not None else m
 
-    def ist_mlp(self, q_ist: torch.Tensor, matches: Dict[str, torch.Tensor]):
-        q_ist = _f32(q_ist, self.device).contiguous()
-        B = self._B
-        assert q_ist.shape == (B, C_IST, 16, 16), tuple(q_ist.shape)
-        rel_scale = self._empty((B, self.k, P), torch.float32)
-        rel_inplane = self._empty((B, self.k, P, 2), torch.float32)
+    def ist_mlp(self, q_ist: torch.Tensor, matches: Dict[str, torch.Tensor], b0: int = 0):
+        """Row a5 for the detections [b0, b0+n) of the staged batch; `q_ist` [n,256,16,16] and `matches` are
+        window-relative (n = their leading dimension)."""
+        q_ist, layout = _ist_layout(_f32(q_ist, self.device))
+        n = q_ist.shape[0]
+        assert matches["id_src"].shape[0] == n
+        rel_scale = self._empty((n, self.k, P), torch.float32)
+        rel_inplane = self._empty((n, self.k, P, 2), torch.float32)
         ms = self._matches_struct(matches)
-        check(self.lib.gp_ist_mlp(self._h, B, q_ist.data_ptr(), C.byref(ms), rel_scale.data_ptr(),
+        check(self.lib.gp_ist_mlp(self._h, b0, n, q_ist.data_ptr(), layout, C.byref(ms), rel_scale.data_ptr(),
                                   rel_inplane.data_ptr(), self.stream))
         return rel_scale, rel_inplane
 
@@ -282,9 +307,13 @@ class Engine:
                       self.cfg.pixel_threshold, self.cfg.patch_size, self.stream)
         return r
 
-    def sort_and_pose(self, q_K, q_M, matches, rel_scale, rel_inplane, ransac) -> Dict[str, torch.Tensor]:
-        B, k = self._B, self.k
+    def sort_and_pose(self, q_K, q_M, matches, rel_scale, rel_inplane, ransac, b0: int = 0,
+                      sort_by_inliers: bool = True) -> Dict[str, torch.Tensor]:
+        """Rows a8 + a9 for the detections [b0, b0+n) of the staged batch (all tensors window-relative)."""
+        k = self.k
+        B = matches["id_src"].shape[0]
         q_K, q_M = _f32(q_K, self.device).contiguous(), _f32(q_M, self.device).contiguous()
+        assert q_K.shape[0] == B and q_M.shape[0] == B
         out = self._alloc_matches(B)
         out.update(relScale=self._empty((B, k, P), torch.float32), relInplane=self._empty((B, k, P, 2), torch.float32))
         ro = self._alloc_ransac(B)
@@ -294,10 +323,33 @@ class Engine:
         pred = GpPredictions(self._matches_struct(out), out["relScale"].data_ptr(), out["relInplane"].data_ptr(),
                              self._ransac_struct(out), out["scores"].data_ptr(), out["pred_poses"].data_ptr())
         ms, rs = self._matches_struct(matches), self._ransac_struct(ransac)
-        check(self.lib.gp_sort_and_pose(self._h, B, q_K.data_ptr(), q_M.data_ptr(), C.byref(ms), rel_scale.data_ptr(),
-                                        rel_inplane.data_ptr(), C.byref(rs), C.byref(pred), self.stream))
+        check(self.lib.gp_sort_and_pose(self._h, b0, B, 1 if sort_by_inliers else 0, q_K.data_ptr(), q_M.data_ptr(),
+                                        C.byref(ms), rel_scale.data_ptr(), rel_inplane.data_ptr(), C.byref(rs),
+                                        C.byref(pred), self.stream))
         out["idx_failed"] = out["idx_failed"].bool()
         return out
+
+    # ------------------------------------------------------------------------------------------------ multi-GPU
+    def comm_init(self, nccl_comm_ptr: int) -> None:
+        """Binds an ncclComm_t (integer address, e.g. `ProcessGroupNCCL._comm_ptr()`) whose rank / size equal this
+        engine's shard map."""
+        check(self.lib.gp_comm_init(self._h, C.c_void_p(nccl_comm_ptr), self.shard_rank, self.shard_world))
+
+    def allgather(self, send: torch.Tensor, recv: torch.Tensor) -> torch.Tensor:
+        assert send.is_contiguous() and recv.is_contiguous()
+        nbytes = send.numel() * send.element_size()
+        assert recv.numel() * recv.element_size() == nbytes * self.shard_world
+        check(self.lib.gp_allgather(self._h, send.data_ptr(), recv.data_ptr(), nbytes, self.stream))
+        return recv
+
+    def topk_allgather_merge(self, packed: torch.Tensor, rank_stride_bytes: int, slot0: Dict[str, torch.Tensor]):
+        """In-place all-gather of the packed candidate records + global top-k merge (the collective of the search)."""
+        B = self._B
+        m = self._alloc_matches(B)
+        cs, ms = self._cand_struct(dict(slot0, rel_scale=None, rel_inplane=None)), self._matches_struct(m)
+        check(self.lib.gp_topk_allgather_merge(self._h, B, packed.data_ptr(), rank_stride_bytes, C.byref(cs),
+                                               C.byref(ms), self.stream))
+        return m
 
     def retrieve(self, q_feat, q_mask, q_obj, q_ist, q_K, q_M, norm_passes: int = 1) -> Dict[str, torch.Tensor]:
         """Rows a3-a9 for one batch on one GPU: the tensor content of GigaPose.eval_retrieval (gigaPose.py:497-604)."""

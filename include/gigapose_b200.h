@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GP_ABI_VERSION 1
+#define GP_ABI_VERSION 2
 #define GP_NUM_PATCHES 256   /* 16 x 16 patches of a 224 x 224 crop, patch size 14 */
 #define GP_AE_DIM 1024       /* DINOv2 ViT-L/14 descriptor size (configs/model/ae_net/dinov2_l.yaml:10) */
 #define GP_IST_DIM 256       /* IST descriptor size (configs/model/ist_net/resnet.yaml:3) */
@@ -64,6 +64,10 @@ typedef struct gp_config {
   float pixel_threshold;      /* RANSAC inlier threshold in pixels (poses.py:18) */
   int32_t patch_size;         /* 14 */
   int32_t precision;          /* GP_PRECISION_* */
+  int32_t ist_bank_global;    /* 0: the IST feature bank holds this handle's templates (slots as in gp_bank_write);
+                                 1: it holds ALL num_templates_global templates of every object, indexed by GLOBAL id and
+                                 written with gp_bank_write_ist -- multi-GPU: descriptors are sharded, the 4x smaller IST
+                                 bank is replicated so that any rank can run row a5 for any global winner */
 } gp_config_t;
 
 const char* gp_last_error(void);
@@ -86,6 +90,10 @@ int gp_destroy(gp_handle_t h);
  *   ist_feat  f32  [n, 256, 16, 16] IST backbone features (gigaPose.py:376), may be NULL if a5 is not used */
 int gp_bank_write(gp_handle_t h, int obj, int tmpl0, int n, const float* feat, int feat_layout, int norm_passes,
                   const float* mask, int H, int W, const float* ist_feat, void* stream);
+/* IST features only: `n` templates of object `obj` starting at IST-bank slot `tmpl0` (a GLOBAL template id when
+ * cfg.ist_bank_global = 1).  ist_layout: GP_LAYOUT_CHANNEL_MAJOR [n,256,16,16] (ISTNet.forward_by_chunk's shape) or
+ * GP_LAYOUT_PATCH_MAJOR [n,256 patches,256 channels] (what gp_ist_trunk_forward writes: stored as is). */
+int gp_bank_write_ist(gp_handle_t h, int obj, int tmpl0, int n, const float* ist_feat, int ist_layout, void* stream);
 
 /* Pose tables over GLOBAL template ids (ObjectPoseRecovery ctor, poses.py:13-24):
  *   K [O,3,3], M [O,Tg,3,3], poses [O,Tg,4,4], all f32. */
@@ -132,11 +140,14 @@ int gp_topk_merge(gp_handle_t h, int B, int G, const gp_candidates_t* gathered, 
 /* Single-GPU convenience: gp_sim_candidates into the workspace + gp_topk_merge(G=1) == LocalSimilarity.test. */
 int gp_sim_topk(gp_handle_t h, int B, const gp_matches_t* out, void* stream);
 
-/* ISTNet.inference for all k hypotheses (ist_net.py:97-120; k-loop gigaPose.py:545-575).
- *   q_ist f32 [B,256,16,16]; outputs rel_scale [B,k,256], rel_inplane [B,k,256,2] (-1000 where invalid).
- * Every template named in m->id_src must be held by this handle. */
-int gp_ist_mlp(gp_handle_t h, int B, const float* q_ist, const gp_matches_t* m, float* rel_scale, float* rel_inplane,
-               void* stream);
+/* ISTNet.inference for all k hypotheses (ist_net.py:97-120; k-loop gigaPose.py:545-575) of the `n` detections
+ * [b0, b0 + n) of the staged batch (b0 = 0, n = B: the whole batch; multi-GPU ranks each take a window).  All tensor
+ * arguments are WINDOW-relative:
+ *   q_ist f32 [n,256,16,16] (GP_LAYOUT_CHANNEL_MAJOR) or [n,256 patches,256] (GP_LAYOUT_PATCH_MAJOR);
+ *   outputs rel_scale [n,k,256], rel_inplane [n,k,256,2] (-1000 where invalid).
+ * Every template named in m->id_src must be in this handle's IST bank (all are when cfg.ist_bank_global = 1). */
+int gp_ist_mlp(gp_handle_t h, int b0, int n, const float* q_ist, int ist_layout, const gp_matches_t* m, float* rel_scale,
+               float* rel_inplane, void* stream);
 
 typedef struct gp_ransac_out {   /* ObjectPoseRecovery.forward_ransac (poses.py:124-163) */
   float* M;                      /* [B,k,3,3] */
@@ -167,11 +178,26 @@ typedef struct gp_predictions {  /* every [B,k,...] tensor after the re-sort of 
   float* poses;                  /* [B,k,4,4] (poses.py:103-122) */
 } gp_predictions_t;
 
-/* scores, stable descending re-sort of the k hypotheses and pose lifting (gigaPose.py:588-604).
- *   q_K, q_M f32 [B,3,3] query intrinsics / crop matrices. */
-int gp_sort_and_pose(gp_handle_t h, int B, const float* q_K, const float* q_M, const gp_matches_t* m,
-                     const float* rel_scale, const float* rel_inplane, const gp_ransac_out_t* r,
+/* scores, stable descending re-sort of the k hypotheses (skipped when sort_by_inliers = 0: the reference's
+ * `sort_pred_by_inliers=False`, gigaPose.py:590) and pose lifting (gigaPose.py:588-604) for the detections
+ * [b0, b0 + n) of the staged batch; every tensor argument is window-relative.
+ *   q_K, q_M f32 [n,3,3] query intrinsics / crop matrices. */
+int gp_sort_and_pose(gp_handle_t h, int b0, int n, int sort_by_inliers, const float* q_K, const float* q_M,
+                     const gp_matches_t* m, const float* rel_scale, const float* rel_inplane, const gp_ransac_out_t* r,
                      const gp_predictions_t* out, void* stream);
+
+/* --- row e: multi-GPU (no reference code: inference is single-GPU, configs/machine/trainer/local.yaml:4) ----------
+ * One process per GPU; rank r holds the descriptor shard {tau : tau % world == r} (cfg.template_id_stride / offset). */
+/* Binds an NCCL communicator (an `ncclComm_t`, e.g. torch's ProcessGroupNCCL communicator) to the handle.  The NCCL
+ * entry points are resolved from the already loaded libnccl at run time (no link-time dependency). */
+int gp_comm_init(gp_handle_t h, void* nccl_comm, int rank, int world);
+/* ncclAllGather of `bytes_per_rank` bytes on `stream`: recv = [world][bytes_per_rank]; send may alias its own slot. */
+int gp_allgather(gp_handle_t h, const void* send, void* recv, size_t bytes_per_rank, void* stream);
+/* THE collective of the search: `packed` = [world][rank_stride_bytes] holds this rank's candidate records (written by
+ * gp_sim_candidates into slot `rank`); all-gathers it in place over NVLink and merges the world * k candidates per
+ * detection into the global top-k (gp_topk_merge semantics).  `slot0` = field pointers of slot 0 inside `packed`. */
+int gp_topk_allgather_merge(gp_handle_t h, int B, void* packed, size_t rank_stride_bytes, const gp_candidates_t* slot0,
+                            const gp_matches_t* out, void* stream);
 
 /* --- row a1: DINOv2 ViT-L/14 patch tokens (AENet.forward_by_chunk, ae_net.py:55-69; hub module un-vendored) ---- */
 typedef struct gp_vit_context* gp_vit_handle_t;

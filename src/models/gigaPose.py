@@ -35,6 +35,35 @@ class _HostResult:
         return self._poses, self._scores
 
 
+def object_indices(infos, num_objects: int) -> np.ndarray:
+    """0-based object indices from the `label` column (1-based ids as strings, gigaPose.py:514-520).  The reference
+    indexes `template_data.ae_features[label - 1]`: label 0 silently wraps to the last object and label > O raises;
+    here both raise (the kernels index the resident bank with these values)."""
+    idx = np.asarray(infos.label).astype(np.int64) - 1
+    if idx.size and (idx.min() < 0 or idx.max() >= num_objects):
+        bad = sorted(set((idx[(idx < 0) | (idx >= num_objects)] + 1).tolist()))
+        raise IndexError(f"object labels {bad} outside [1, {num_objects}] (the onboarded bank has {num_objects} objects)")
+    return idx
+
+
+def weights_fingerprint(*modules) -> str:
+    """Content hash of every parameter / buffer of the encoders (two moments per tensor, one device->host copy):
+    the on-disk bank cache is only valid for the weights it was encoded with."""
+    import hashlib
+    h = hashlib.sha1()
+    sums = []
+    for m in modules:
+        for name, t in list(m.named_parameters()) + list(m.named_buffers()):
+            h.update(name.encode())
+            h.update(str(tuple(t.shape)).encode())
+            if t.numel() and t.is_floating_point():
+                d = t.detach().double()
+                sums.append(torch.stack([d.sum(), d.abs().sum()]))
+    if sums:
+        h.update(torch.stack(sums).cpu().numpy().tobytes())
+    return h.hexdigest()[:16]
+
+
 class GigaPose(LightningModule):
     def __init__(self, model_name, ae_net, ist_net, training_loss, testing_metric, optim_config, log_interval, log_dir,
                  max_num_dets_per_forward=None, test_setting="localization", **kwargs):
@@ -96,10 +125,20 @@ class GigaPose(LightningModule):
         cache = None
         if getattr(self, "bank_cache_dir", None):
             os.makedirs(self.bank_cache_dir, exist_ok=True)
+            # the file is bound to the encoder weights and to the template content (first object's crops + masks): a
+            # cache written with another checkpoint, or stale renders under the same dataset name, is not loaded
+            content = torch.stack([first.rgb.double().sum(), first.mask.double().sum()]).cpu().numpy().tobytes().hex()[:16]
+            eng.fingerprint = weights_fingerprint(self.ae_net, self.ist_net.backbone) + "-" + content + \
+                f"-{tuple(first.mask.shape[-2:])}"
             cache = osp.join(self.bank_cache_dir, f"{dataset_name}_{n_obj}x{T}_{eng.precision}.gpbank")
-        cached = cache is not None and osp.exists(cache)
-        if cached:
-            eng.load_bank(cache)
+        cached = False
+        if cache is not None and osp.exists(cache):
+            from gigapose_b200._lib import GigaPoseNativeError
+            try:
+                eng.load_bank(cache)
+                cached = True
+            except GigaPoseNativeError as e:           # other weights / shape / ABI: rebuild and overwrite
+                logger.info(f"bank cache {cache} not usable ({e}); re-encoding the templates")
         for idx in range(n_obj):
             data = first if idx == 0 else dataset[idx]
             if not cached:
@@ -152,7 +191,7 @@ class GigaPose(LightningModule):
 
     # ------------------------------------------------------------------ the hot path (gigaPose.py:481-633)
     @torch.no_grad()
-    def _retrieve_chunk(self, eng, tar_img, tar_mask, q_obj, tar_K, tar_M, mark=lambda name: None):
+    def _retrieve_chunk(self, eng, tar_img, tar_mask, q_obj, tar_K, tar_M, mark=lambda name: None, sort=True):
         """Rows a1, a3-a9 for at most `eng.max_batch` detections; every step is a kernel launch on the current
         stream, no host synchronisation -> capturable as a CUDA graph."""
         mark("start")
@@ -166,14 +205,14 @@ class GigaPose(LightningModule):
         rel_scale, rel_inplane = eng.ist_mlp(tar_ist, m)
         mark("a5_ist_mlp")
         r = eng.ransac(m, rel_scale, rel_inplane)
-        out = eng.sort_and_pose(tar_K, tar_M, m, rel_scale, rel_inplane, r)
+        out = eng.sort_and_pose(tar_K, tar_M, m, rel_scale, rel_inplane, r, sort_by_inliers=sort)
         mark("a7_a8_a9_ransac_sort_pose")
         return out
 
-    def _graphed_chunk(self, eng, dataset_name, tar_img, tar_mask, q_obj, tar_K, tar_M):
-        """Static input buffers + one captured graph per (dataset, batch size); outputs are the graph's static tensors
-        (valid until the next replay with the same batch size)."""
-        key = (dataset_name, tar_img.shape[0])
+    def _graphed_chunk(self, eng, dataset_name, tar_img, tar_mask, q_obj, tar_K, tar_M, sort=True):
+        """Static input buffers + one captured graph per (dataset, batch size); outputs are copies of the graph's
+        static tensors."""
+        key = (dataset_name, tar_img.shape[0], bool(sort))
         entry = self._graphs.get(key)
         if entry is None:
             static = [t.clone() for t in (tar_img, tar_mask, q_obj, tar_K, tar_M)]
@@ -181,18 +220,20 @@ class GigaPose(LightningModule):
             side.wait_stream(torch.cuda.current_stream(eng.device))
             with torch.cuda.stream(side):
                 for _ in range(2):                                           # warm-up outside the capture
-                    self._retrieve_chunk(eng, *static)
+                    self._retrieve_chunk(eng, *static, sort=sort)
             torch.cuda.current_stream(eng.device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                out = self._retrieve_chunk(eng, *static)
+                out = self._retrieve_chunk(eng, *static, sort=sort)
             entry = (graph, static, out)
             self._graphs[key] = entry
         graph, static, out = entry
         for dst, src in zip(static, (tar_img, tar_mask, q_obj, tar_K, tar_M)):
             dst.copy_(src, non_blocking=True)
         graph.replay()
-        return out
+        # the graph's static output tensors are overwritten by the next replay of the same batch size (the next chunk
+        # of this call, or the next call): hand out copies (110 KB per detection)
+        return {k: v.clone() for k, v in out.items()}
 
     def stage(self, batch, dataset_name):
         """Start the host->device copy of a (pinned) batch on a dedicated copy stream and return the device-resident
@@ -206,7 +247,7 @@ class GigaPose(LightningModule):
         with torch.cuda.stream(self._copy_stream):
             staged = tc.PandasTensorCollection(infos=batch.infos, **{k: v.to(device, non_blocking=True)
                                                                      for k, v in batch._tensors.items()})
-            labels = torch.from_numpy(np.asarray(batch.infos.label).astype(np.int64) - 1).pin_memory()
+            labels = torch.from_numpy(object_indices(batch.infos, self.engines[dataset_name].O)).pin_memory()
             staged._q_obj = labels.to(device, non_blocking=True)          # object indices (gigaPose.py:514-520)
             staged._q_obj_host = labels                                    # keeps the pinned source alive until the copy ran
             ready = torch.cuda.Event()
@@ -238,7 +279,7 @@ class GigaPose(LightningModule):
         return _HostResult(out[0], out[1], done)
 
     @torch.no_grad()
-    def retrieve(self, batch, dataset_name):
+    def retrieve(self, batch, dataset_name, sort_pred_by_inliers=True):
         """Rows a1, a3-a9 for one batch; returns the PandasTensorCollection `eval_retrieval` builds."""
         if dataset_name not in self.engines:
             self.set_template_data(dataset_name)
@@ -255,7 +296,7 @@ class GigaPose(LightningModule):
         if ready is not None:
             q_obj = batch._q_obj                         # uploaded with the batch: no blocking pageable copy here
         else:
-            q_obj = torch.as_tensor(np.asarray(batch.infos.label).astype(np.int64) - 1, device=device)   # gigaPose.py:514-520
+            q_obj = torch.as_tensor(object_indices(batch.infos, eng.O), device=device)   # gigaPose.py:514-520
         tar_K, tar_M = batch.tar_K.to(device).float(), batch.tar_M.to(device).float()
         outs = []
         B = tar_img.shape[0]
@@ -273,9 +314,9 @@ class GigaPose(LightningModule):
             sl = slice(b0, min(B, b0 + eng.max_batch))
             args = (tar_img[sl], tar_mask[sl], q_obj[sl], tar_K[sl], tar_M[sl])
             if self.use_cuda_graph and not self.profile_stages:
-                outs.append(self._graphed_chunk(eng, dataset_name, *args))
+                outs.append(self._graphed_chunk(eng, dataset_name, *args, sort=sort_pred_by_inliers))
             else:
-                outs.append(self._retrieve_chunk(eng, *args, mark=mark))
+                outs.append(self._retrieve_chunk(eng, *args, mark=mark, sort=sort_pred_by_inliers))
         ev[1].record()
         if self.profile_stages:
             torch.cuda.synchronize(device)
@@ -288,7 +329,7 @@ class GigaPose(LightningModule):
         return tc.PandasTensorCollection(infos=batch.infos, **out)
 
     def eval_retrieval(self, batch, idx_batch, dataset_name, sort_pred_by_inliers=True):
-        predictions = self.retrieve(batch, dataset_name)
+        predictions = self.retrieve(batch, dataset_name, sort_pred_by_inliers=sort_pred_by_inliers)
         ev = self._events
         ev[1].synchronize()
         # CUDA-event time of the whole retrieval.  (The reference's wall-clock timer is overwritten between its two

@@ -24,6 +24,8 @@ class AENet(LightningModule):
         self.descriptor_size = descriptor_size
         self.max_batch_size = max_batch_size
         self.patch_size = patch_size
+        # "fp32_split" (3-pass bf16 hi/lo products, fp32-faithful) | "bf16" (1 pass); None = GIGAPOSE_VIT_PRECISION / default
+        self.precision = kwargs.get("precision", None)
 
     def get_toUpdate_parameters(self):
         return self.dinov2_model.parameters()
@@ -34,7 +36,8 @@ class AENet(LightningModule):
         from gigapose_b200.vit_engine import vit_forward_features
         outs = []
         for i in range(0, images.shape[0], self.max_batch_size):
-            tok = vit_forward_features(self.dinov2_model, images[i:i + self.max_batch_size])[:, 1:, :]
+            tok = vit_forward_features(self.dinov2_model, images[i:i + self.max_batch_size],
+                                       precision=getattr(self, "precision", None))[:, 1:, :]
             outs.append(tok)
         tok = torch.cat(outs, 0) if len(outs) > 1 else outs[0]
         return F.normalize(tok, dim=2)

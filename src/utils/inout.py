@@ -147,3 +147,11 @@ def save_predictions_from_batched_predictions(prediction_dir, dataset_name, mode
         path = osp.join(prediction_dir, f"{stem}MultiHypothesis.csv")
         save_bop_results(path, calculate_runtime_per_image(topk, is_refined=is_refined), additional_name="instance_id")
         logger.info(f"Saved predictions to {path}")
+
+
+
+# everything this file does not provide (the CNOS-detection / test-list loaders the reference's dataloaders import from
+# `src.utils.inout`) comes from the reference checkout's own `src/utils/inout.py` when one is on the path
+import src as _src  # noqa: E402
+
+__getattr__ = _src.fallback_getattr(__name__)

@@ -28,8 +28,6 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
 def test_rows_config_lists_every_native_row():
     sys.path.insert(0, ROOT)
     import bench
-    native = bench.rows_config("native")
+    native = bench.rows_config()
     assert native["library_rows"] == [] and len(native["native_rows"]) == 9
     assert any(r.startswith("a6") for r in native["native_rows"])
-    cudnn = bench.rows_config("cudnn")
-    assert len(cudnn["library_rows"]) == 1 and not any(r.startswith("a6") for r in cudnn["native_rows"])

@@ -1,0 +1,166 @@
+"""-m gpu: parity of the WHOLE hot path against the CPU oracle, from crops to poses and on every BASELINE.json
+configuration shape.
+
+* crop level (reference `src/models/gigaPose.py:497-604`): the same 224x224 crops go through
+  `port.ae_features` + `port.ISTBackbonePort` + `port.retrieval` on the CPU and through `GigaPose.retrieve` (native ViT-L/14,
+  native IST trunk, resident bank, fused similarity search, MLP, RANSAC, pose) on the GPU; template ids, patch
+  correspondences and RANSAC inlier sets must be EQUAL, poses within 1e-3 -- for the fp32-faithful (`fp32_split`)
+  ViT.  The plain-bf16 ViT runs through the same comparison and its flip counts are reported (not asserted): that is
+  the measurement which justifies paying 3 tensor passes in the ViT linears.
+* feature level, full a4-a9 chain against the oracle on slices of c2 (8 x 162, B=32), c3 (30 x 162, B=64),
+  c4 (21 x 162, B=128) and a T=576 bank (the c5 template count).
+"""
+import os
+import sys
+
+import pandas as pd
+import pytest
+import torch
+
+from gigapose_b200 import synth
+from oracle import port
+
+from helpers import INT_KEYS, assert_chain_equal, cpu, engine_from_case, reference_slice, run_engine, write_report
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------------------------------------------- crop level
+def _models_with_oracle_weights():
+    """Native modules carrying exactly the oracle's (seeded) weights."""
+    import src.megapose.utils.tensor_collection as tc  # noqa: F401
+    from gigapose_b200.vit import DinoVisionTransformer
+    from src.models.gigaPose import GigaPose
+    from src.models.matching import LocalSimilarity
+    from src.models.network.ae_net import AENet
+    from src.models.network.ist_net import ISTNet, Regressor
+    from src.models.network.resnet import ResNet
+    ref_vit = port.DinoV2Port(depth=24, seed=7)
+    ref_bb = port.ISTBackbonePort()
+    ref_reg = port.RegressorPort(seed=12)
+    vit = DinoVisionTransformer(depth=24)
+    vit.load_state_dict(ref_vit.state_dict())
+    ae = AENet("dinov2_vitl14", dinov2_model=vit, descriptor_size=1024, max_batch_size=64)
+    backbone = ResNet(dict(n_heads=0, input_dim=3, input_size=256, initial_dim=128, block_dims=[128, 192, 256, 512],
+                           descriptor_size=256))
+    reg = Regressor(descriptor_size=256, hidden_dim=256, use_tanh_act=True, normalize_output=True)
+    ist = ISTNet("resnet", backbone, reg, max_batch_size=64)
+    ist.backbone.load_state_dict(ref_bb.state_dict())          # ISTNet re-initialises conv / linear layers
+    ist.regressor.load_state_dict(ref_reg.state_dict())
+    metric = LocalSimilarity(k=5, sim_threshold=0.5, patch_threshold=3)
+    model = GigaPose("large", ae, ist, training_loss=None, testing_metric=metric, optim_config=None, log_interval=1000,
+                     log_dir=os.path.join(ROOT, "gpurun_out", "test_logs"), max_num_dets_per_forward=None)
+    return model.to(DEV).eval(), ref_vit, ref_bb, ref_reg
+
+
+def _count_flips(out, ref):
+    flips = {}
+    for k in ("id_src", "src_pts", "tar_pts", "ransac_scores", "ransac_src_pts", "idx_failed"):
+        flips[k] = int((out[k].to(ref[k].dtype) != ref[k]).sum())
+    err = (out["pred_poses"] - ref["pred_poses"]).abs()
+    err[..., :3, 3] /= ref["pred_poses"][..., :3, 3].abs().clamp(min=1.0)
+    same_tmpl = (out["id_src"] == ref["id_src"])
+    flips["pose_err_max_same_template"] = float(err[same_tmpl].max()) if same_tmpl.any() else None
+    flips["score_src_err_max"] = float((out["score_src"] - ref["score_src"]).abs().max())
+    flips["top1_template_flips"] = int((out["id_src"][:, 0] != ref["id_src"][:, 0]).sum())
+    return flips
+
+
+def test_crop_level_chain_matches_oracle():
+    sys.path.insert(0, ROOT)
+    import bench
+    O, T, B = 2, 10, 6
+    model, ref_vit, ref_bb, ref_reg = _models_with_oracle_weights()
+    templates = bench.SyntheticTemplates(O, T, torch.device("cpu"))
+    model.template_datasets = {"synthetic": templates}
+    model.test_dataset_name = "synthetic"
+    batch, labels, views = bench.make_queries(templates, B, seed=3)
+
+    # ---- CPU oracle from the same crops (gigaPose.py:357-398 onboarding, :497-604 retrieval)
+    torch.set_num_threads(max(1, min(32, os.cpu_count() or 1)))
+    rgbs, masks = zip(*[templates.crops(o) for o in range(O)])
+    rgb_all = torch.cat(rgbs)                                                  # [O*T,3,224,224]
+    src_ae = port.ae_features(ref_vit, rgb_all).reshape(O, T, 1024, 16, 16)
+    with torch.no_grad():
+        src_ist = ref_bb(rgb_all).reshape(O, T, 256, 16, 16)
+        tar_ist = ref_bb(batch.tar_img)
+    tar_ae = port.ae_features(ref_vit, batch.tar_img)
+    lab = labels - 1
+    ref_in = dict(src_feats=src_ae[lab], tar_feat=tar_ae, src_masks=torch.stack(masks)[lab], tar_mask=batch.tar_mask,
+                  src_ist=src_ist[lab], tar_ist=tar_ist, tar_label=labels, tar_K=batch.tar_K, tar_M=batch.tar_M,
+                  template_K=templates.K.repeat(O, 1, 1), template_Ms=templates.M, template_poses=templates.poses.repeat(O, 1, 1, 1))
+    ref = port.retrieval(ref_in, ref_reg)
+    n_valid = int((ref["src_pts"][..., 0] != -1).sum())
+    assert n_valid > 50 * B, "degenerate workload: almost no valid correspondences"
+
+    # ---- GPU, both ViT precisions through the reference-facing module
+    report = {"workload": f"{B} query crops vs {O} objects x {T} templates, ViT-L/14 depth 24, oracle-seeded weights",
+              "valid_correspondences": n_valid, "hypotheses": B * 5}
+    outs = {}
+    for prec in ("fp32_split", "bf16"):
+        model.ae_net.precision = prec
+        model.engines.clear()
+        pred = model.retrieve(batch, "synthetic")
+        out = cpu({k: getattr(pred, k) for k in INT_KEYS + ["score_src", "score_pts", "relScale", "relInplane", "M",
+                                                            "scores", "pred_poses"]})
+        outs[prec] = out
+        report[prec] = _count_flips(out, ref)
+    model.ae_net.precision = None
+    print("\ncrop-level flip counts:", report)
+    write_report("crop_chain_parity.json", report)
+    assert_chain_equal(outs["fp32_split"], ref, tag="crop-level fp32_split: ")
+
+
+# ------------------------------------------------------------------------------------- feature level, BASELINE shapes
+def _chain_on_slice(case, reg, sel, tag, max_batch=None):
+    eng = engine_from_case(case, regressor=reg, max_batch=max_batch)
+    out = cpu(run_engine(eng, case))
+    ref = port.retrieval(reference_slice(case, sel), reg)
+    assert_chain_equal(out, ref, sel=sel, tag=tag)
+    return out
+
+
+def test_c2_full_chain_matches_oracle_on_a_slice():
+    case = synth.make_feature_case(B=32, O=8, T=162, seed=42)
+    _chain_on_slice(case, port.RegressorPort(seed=9), [0, 9, 17, 31], "c2: ")
+
+
+@pytest.mark.parametrize("name,O,B,sel", [("c3", 30, 64, [1, 40, 63]), ("c4", 21, 128, [0, 77, 127])])
+def test_c3_c4_shaped_chain_matches_oracle_on_a_slice(name, O, B, sel):
+    """BASELINE.json configs[2], configs[3] on ONE GPU (whole bank resident: 5.1 / 3.6 GB); the bank is generated on
+    the device, the oracle sees the selected queries and the full 162-template banks of their objects."""
+    case = synth.make_feature_case(B=B, O=O, T=162, seed=50 + O, device=DEV, obj_chunk=2)
+    _chain_on_slice(case, port.RegressorPort(seed=10), sel, name + ": ")
+
+
+def test_t576_chain_matches_oracle():
+    """The c5 template count (576 per object): odd number of 32-query chunks per template, 18 top-k tiles."""
+    case = synth.make_feature_case(B=6, O=3, T=576, seed=61, device=DEV, obj_chunk=1)
+    _chain_on_slice(case, port.RegressorPort(seed=11), [0, 3, 5], "T=576: ")
+
+
+def test_cuda_graph_with_more_than_one_chunk():
+    """B = 2 x max_dets_per_call through the CUDA graph must equal the eager result (every chunk's outputs
+    are copied out of the graph's static tensors before the next replay)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    model = bench.build_models(torch.device(DEV))
+    model.max_dets_per_call = 4
+    templates = bench.SyntheticTemplates(2, 8, torch.device(DEV))
+    model.template_datasets = {"synthetic": templates}
+    model.test_dataset_name = "synthetic"
+    batch, labels, views = bench.make_queries(templates, 8, seed=6)
+    model.use_cuda_graph = False
+    eager = model.retrieve(batch, "synthetic")
+    model.use_cuda_graph = True
+    for _ in range(2):
+        graphed = model.retrieve(batch, "synthetic")
+    for k in ("id_src", "src_pts", "scores", "pred_poses"):
+        assert torch.equal(getattr(graphed, k).cpu(), getattr(eager, k).cpu()), k
+    # a result stays valid after the next call
+    keep = graphed.pred_poses.clone()
+    other, _, _ = bench.make_queries(templates, 8, seed=7)
+    model.retrieve(other, "synthetic")
+    assert torch.equal(graphed.pred_poses, keep)

@@ -140,23 +140,28 @@ def test_gigapose_module_end_to_end_small():
             assert torch.equal(scores_host, pred.scores.cpu())
 
 
-@pytest.mark.parametrize("backend,tol", [("native", 3e-4), ("cudnn", 3e-3)])
-def test_ist_backbone_matches_oracle(golden_dir, backend, tol):
-    """Row a6 against the fp32 CPU oracle's golden features.  native: tcgen05 implicit-GEMM trunk with fp32-faithful
-    split products (observed 7e-5 of the feature range after 21 layers).  cudnn: the BN-folded library path, whose
-    convolutions run in TF32 by torch's default (the reference's own GPU behaviour), hence 3e-3."""
+def test_ist_backbone_matches_oracle(golden_dir, tol=3e-4):
+    """Row a6 against the fp32 CPU oracle's golden features: tcgen05 implicit-GEMM trunk with fp32-faithful split
+    products (observed 7e-5 of the feature range after 21 layers).  There is no library / CPU path to fall back to:
+    a CPU tensor or another crop size raises."""
     import os
     import numpy as np
     from src.models.network.resnet import ResNet
     ref = port.ISTBackbonePort()
     net = ResNet(dict(n_heads=0, input_dim=3, input_size=256, initial_dim=128, block_dims=[128, 192, 256, 512],
-                      descriptor_size=256, backend=backend))
+                      descriptor_size=256))
     net.load_state_dict(ref.state_dict())
     net = net.to(DEV).eval()
     rgb, _ = synth.make_crops(2, seed=31)
     with torch.no_grad():
         got = net(rgb.to(DEV)).cpu()
-    assert (getattr(net, "_gp_trunk_engine", None) is not None) == (backend == "native")
+    assert getattr(net, "_gp_trunk_engine", None) is not None
+    from gigapose_b200._lib import GigaPoseNativeError
+    with torch.no_grad():
+        with pytest.raises(GigaPoseNativeError):
+            net(rgb)                                        # CPU tensor
+        with pytest.raises(GigaPoseNativeError):
+            net(torch.zeros(1, 3, 256, 256, device=DEV))    # not a 224x224 crop
     g = np.load(os.path.join(golden_dir, "backbones.npz"))
     want = torch.from_numpy(g["ist_feat_sub"])
     scale = want.abs().max().item()

@@ -90,7 +90,7 @@ def test_ist_trunk_weight_folding_matches_eval_mode_modules():
         for m in net.modules():
             if isinstance(m, torch.nn.BatchNorm2d):
                 m.running_mean.normal_(0, 0.2); m.running_var.uniform_(0.5, 1.5); m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.2)
-    assert ist_trunk.supports(net) and net.backend == "native"
+    assert ist_trunk.supports(net)
     convs = ist_trunk.folded_convs_in_abi_order(net, "cpu")
     assert len(convs) == ist_trunk.NUM_CONVS == 21
     shapes = [tuple(w.shape) for w, _ in convs]
