@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -84,6 +85,13 @@ int gp_internal_fail(int code, const char* fmt, ...) {
   return code;
 }
 void gp_internal_count_launches(int n) { g_launches += n; }
+namespace gp {
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* ev = getenv("GIGAPOSE_PDL"); v = ev ? (ev[0] != '0') : 1; }
+  return v != 0;
+}
+}  // namespace gp
 
 // generic 2-D bf16 plane map [rows, cols] (cols contiguous) with explicit box and swizzle (64 or 128 = box_cols * 2 bytes)
 int gp_internal_make_map_ex(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows,
@@ -230,6 +238,8 @@ struct gp_context {
   Bank bank;
   Workspace ws;
   CUtensorMap tm_q_hi, tm_q_lo, tm_t_hi, tm_t_lo;
+  CUtensorMap tm_t_hi128, tm_t_lo128;   // 128-row boxes: each CTA of a pair stages half of a template slab
+  int sim_pair;      // similarity kernel on 2-CTA clusters (GIGAPOSE_SIM_PAIR, default on)
   gp::IstMlpWeights mlp;
   bool mlp_set;
   int cur_B;      // batch size staged by gp_set_queries (0 = none)
@@ -297,6 +307,10 @@ int gp_create(const gp_config_t* cfg, void* bank_mem, void* workspace_mem, gp_ha
   h->num_sms = prop.multiProcessorCount;
   h->mlp_set = false;
   h->cur_B = 0;
+  {
+    const char* ev = getenv("GIGAPOSE_SIM_PAIR");
+    h->sim_pair = ev ? (ev[0] != '0') : 0;
+  }
   h->nccl_comm = nullptr;
   h->rank = 0;
   h->world = 1;
@@ -307,6 +321,7 @@ int gp_create(const gp_config_t* cfg, void* bank_mem, void* workspace_mem, gp_ha
   const uint64_t q_rows = (uint64_t)cfg->max_batch;
   int e;
   if ((e = make_plane_map(&h->tm_t_hi, h->bank.hi, bank_rows, 256)) || (e = make_plane_map(&h->tm_t_lo, h->bank.lo, bank_rows, 256)) ||
+      (e = make_plane_map(&h->tm_t_hi128, h->bank.hi, bank_rows, 128)) || (e = make_plane_map(&h->tm_t_lo128, h->bank.lo, bank_rows, 128)) ||
       (e = make_plane_map(&h->tm_q_hi, h->ws.q_hi, q_rows, 128)) || (e = make_plane_map(&h->tm_q_lo, h->ws.q_lo, q_rows, 128))) {
     delete h;
     return e;
@@ -439,7 +454,11 @@ static int run_sim(gp_context* h, int B, cudaStream_t s, float* debug_tile = nul
   p.rec_idx = h->ws.rec_idx;
   p.rec_valid = h->ws.rec_valid;
   p.debug_tile = debug_tile;
-  GP_CUDA(gp::launch_sim_search(h->tm_q_hi, h->tm_q_lo, h->tm_t_hi, h->tm_t_lo, p, h->num_sms, s));
+  p.pair = h->sim_pair;
+  if (p.pair)
+    GP_CUDA(gp::launch_sim_search(h->tm_q_hi, h->tm_q_lo, h->tm_t_hi128, h->tm_t_lo128, p, h->num_sms, s));
+  else
+    GP_CUDA(gp::launch_sim_search(h->tm_q_hi, h->tm_q_lo, h->tm_t_hi, h->tm_t_lo, p, h->num_sms, s));
   g_launches += 1;
   return GP_OK;
 }

@@ -6,6 +6,30 @@
 
 namespace gp {
 
+// Launch helper shared by the .cu files: optional 2-CTA cluster and optional programmatic dependent launch
+// (GIGAPOSE_PDL=0 turns the latter off; kernels launched this way call pdl_wait() before touching earlier kernels' data).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                             bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster_x; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl && pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------- similarity search (sim_search.cu)
 struct SimSearchParams {
   int num_items;              // B * T
@@ -23,6 +47,7 @@ struct SimSearchParams {
   uint8_t* rec_idx;           // [B,T,256]  idx_tar2src
   uint8_t* rec_valid;         // [B,T,256]  mask_all != 0
   float* debug_tile;          // nullable [num_items,256,256]: raw fp32 similarity tiles (tests only)
+  int pair;                   // 1: 2-CTA cluster kernel (cta_group::2, one item per pair; template maps with 128-row boxes)
 };
 cudaError_t launch_sim_search(const CUtensorMap& q_hi, const CUtensorMap& q_lo, const CUtensorMap& t_hi,
                               const CUtensorMap& t_lo, const SimSearchParams& p, int num_sms, cudaStream_t stream);

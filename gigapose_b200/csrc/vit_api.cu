@@ -188,6 +188,56 @@ int gp_vit_destroy(gp_vit_handle_t h) {
   return GP_OK;
 }
 
+// diagnostics: the 4 * depth linear layers of one forward over `b` crops, back to back on `stream`, `iters` times,
+// between two CUDA events (synchronises the stream).  Operands are whatever the workspace holds (the GEMM does not
+// care); the residual stream is clobbered and rebuilt by the next gp_vit_forward.
+int gp_vit_time_linears(gp_vit_handle_t h, int b, int iters, float* avg_ms, void* stream) {
+  if (!h || !avg_ms || iters < 1) return gp_internal_fail(GP_ERR_INVALID, "bad argument");
+  if (b < 1 || b > h->max_crops) return gp_internal_fail(GP_ERR_INVALID, "batch %d outside [1, %d]", b, h->max_crops);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int M = b * kTok;
+  auto linear = [&](const Planes& a, const Planes& w, gp::GemmParams& gp_) {
+    gp_.pair = h->pair;
+    return h->pair ? gp::launch_vit_gemm(a.m_hi, a.m_lo, w.p_hi, w.p_lo, gp_, h->num_sms, s)
+                   : gp::launch_vit_gemm(a.m_hi, a.m_lo, w.m_hi, w.m_lo, gp_, h->num_sms, s);
+  };
+  auto run = [&]() -> int {
+    for (int i = 0; i < h->depth; ++i) {
+      const BlockW& B = h->blocks[i];
+      gp::GemmParams g{};
+      g.passes = h->passes; g.M = M; g.N = kQkv; g.K = kDim; g.mode = gp::GEMM_QKV_HEADS; g.bias = B.qkv_b;
+      g.out_hi = h->qkv.hi; g.out_lo = h->qkv.lo; g.tokens_per_img = kTok; g.qkv_crop_stride = h->max_crops;
+      GPV_CUDA(linear(h->ln, B.qkv, g));
+      g = gp::GemmParams{}; g.passes = h->passes;
+      g.M = M; g.N = kDim; g.K = kDim; g.mode = gp::GEMM_SCALE_RESIDUAL; g.bias = B.proj_b; g.gamma = B.ls1; g.x = h->x;
+      GPV_CUDA(linear(h->attn, B.proj, g));
+      g = gp::GemmParams{}; g.passes = h->passes;
+      g.M = M; g.N = kMlp; g.K = kDim; g.mode = gp::GEMM_PLANES_GELU; g.bias = B.fc1_b; g.out_hi = h->hid.hi; g.out_lo = h->hid.lo;
+      GPV_CUDA(linear(h->ln, B.fc1, g));
+      g = gp::GemmParams{}; g.passes = h->passes;
+      g.M = M; g.N = kDim; g.K = kMlp; g.mode = gp::GEMM_SCALE_RESIDUAL; g.bias = B.fc2_b; g.gamma = B.ls2; g.x = h->x;
+      GPV_CUDA(linear(h->hid, B.fc2, g));
+    }
+    return GP_OK;
+  };
+  cudaEvent_t e0, e1;
+  GPV_CUDA(cudaEventCreate(&e0));
+  GPV_CUDA(cudaEventCreate(&e1));
+  if (int e = run()) return e;                       // warm-up
+  GPV_CUDA(cudaEventRecord(e0, s));
+  for (int it = 0; it < iters; ++it)
+    if (int e = run()) return e;
+  GPV_CUDA(cudaEventRecord(e1, s));
+  GPV_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  GPV_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *avg_ms = ms / iters;
+  gp_internal_count_launches(4 * h->depth * (iters + 1));
+  return GP_OK;
+}
+
 int gp_vit_forward(gp_vit_handle_t h, int b, const float* img, float* x_prenorm, void* stream) {
   if (!h || !img || !x_prenorm) return gp_internal_fail(GP_ERR_INVALID, "null argument");
   if (b < 1 || b > h->max_crops) return gp_internal_fail(GP_ERR_INVALID, "batch %d outside [1, %d]", b, h->max_crops);

@@ -77,6 +77,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
                     const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __restrict__ qkv_lo,
                     __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int crop_stride, int passes) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sK[2] = {smem, smem + kKVPlane};                                   // hi, lo
   uint8_t* sV[2] = {smem + 2 * kKVPlane, smem + 3 * kKVPlane};
@@ -104,6 +105,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tail.tmem_base;
+  pdl_wait();                                        // q / k / v planes come from the QKV GEMM launched before
   if (threadIdx.x == 0) STAMP(0);
 
   if (warp == 0) {
@@ -405,12 +407,9 @@ cudaError_t launch_attention_tc(const CUtensorMap& hi128, const CUtensorMap& lo1
     configured = true;
   }
   if (b <= 0) return cudaSuccess;
-  attention_tc_kernel<<<b * kHeads, kThreads, kSmem, s>>>(hi128, lo128, hi16, lo16,
-                                                         reinterpret_cast<const __nv_bfloat16*>(qkv_hi),
-                                                         reinterpret_cast<const __nv_bfloat16*>(qkv_lo),
-                                                         reinterpret_cast<__nv_bfloat16*>(out_hi),
-                                                         reinterpret_cast<__nv_bfloat16*>(out_lo), crop_stride, passes);
-  return cudaGetLastError();
+  return launch_ex(attention_tc_kernel, dim3(b * kHeads), dim3(kThreads), kSmem, s, 1, true, hi128, lo128, hi16, lo16,
+                   reinterpret_cast<const __nv_bfloat16*>(qkv_hi), reinterpret_cast<const __nv_bfloat16*>(qkv_lo),
+                   reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), crop_stride, passes);
 }
 
 }  // namespace gp

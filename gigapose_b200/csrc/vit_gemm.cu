@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();                                     // the next kernel's CTAs may take SMs as this grid's CTAs retire
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   static_assert(!(kSwap && kPair), "the swapped layers have M = 128 filters: nothing to pair");
   constexpr int kNumStages = kPair ? kPairStages : kStages;
@@ -122,6 +123,7 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   if constexpr (kPair) cluster_sync_all();         // barriers and TMEM of the peer exist before anything reaches across
   tc_fence_after();
   const uint32_t tmem_base = tail.tmem_base;
+  pdl_wait();                                        // everything above overlapped the previous kernel's tail
   if (threadIdx.x == 0) GSTAMP(63);
 
   if (warp == 0) {
@@ -469,19 +471,13 @@ cudaError_t launch_vit_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, co
     if (p.conv && p.M % (2 * kBM) != 0) return cudaErrorInvalidValue;
     const int tiles = ((p.M + 2 * kBM - 1) / (2 * kBM)) * (p.N / bn);
     const int clusters = tiles < num_sms / 2 ? tiles : num_sms / 2;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, vit_gemm_kernel<false, true>, a_hi, a_lo, w_hi, w_lo, p);
+    return launch_ex(vit_gemm_kernel<false, true>, dim3(2 * clusters), dim3(kThreads), kSmemBytes, stream, 2, true, a_hi, a_lo,
+                     w_hi, w_lo, p);
   }
   const int tiles = ((p.M + kBM - 1) / kBM) * (p.N / bn);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  if (p.swap) vit_gemm_kernel<true, false><<<grid, kThreads, kSmemBytes, stream>>>(a_hi, a_lo, w_hi, w_lo, p);
-  else vit_gemm_kernel<false, false><<<grid, kThreads, kSmemBytes, stream>>>(a_hi, a_lo, w_hi, w_lo, p);
-  return cudaGetLastError();
+  if (p.swap) return launch_ex(vit_gemm_kernel<true, false>, dim3(grid), dim3(kThreads), kSmemBytes, stream, 1, true, a_hi, a_lo, w_hi, w_lo, p);
+  return launch_ex(vit_gemm_kernel<false, false>, dim3(grid), dim3(kThreads), kSmemBytes, stream, 1, true, a_hi, a_lo, w_hi, w_lo, p);
 }
 
 }  // namespace gp

@@ -91,6 +91,13 @@ class NativeViT:
         return out
 
 
+    def time_linears(self, b: int, iters: int = 5) -> float:
+        """Average milliseconds of the 4 * depth linear layers of one forward over `b` crops (CUDA events, alone)."""
+        ms = C.c_float()
+        check(self.lib.gp_vit_time_linears(self._h, b, iters, C.byref(ms), torch.cuda.current_stream(self.device).cuda_stream))
+        return ms.value
+
+
 @torch.no_grad()
 def vit_forward_features(model, x: torch.Tensor, precision: str = None) -> torch.Tensor:
     """x [b,3,224,224] -> x_prenorm [b,257,1024] (tokens after the last block, before the final norm)."""

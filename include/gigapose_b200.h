@@ -263,6 +263,9 @@ uint64_t gp_launch_count(void);
 /* times `iters` back-to-back runs of the similarity kernel alone with CUDA events on `stream`
  * (synchronises the stream); writes the average milliseconds per launch. */
 int gp_time_sim_kernel(gp_handle_t h, int B, int iters, float* avg_ms, void* stream);
+/* same for the 4 * depth linear layers (vit_gemm_kernel) of one ViT forward over `b` crops: average milliseconds per
+ * forward's worth of linears (the residual stream is clobbered; the next gp_vit_forward rebuilds it). */
+int gp_vit_time_linears(gp_vit_handle_t h, int b, int iters, float* avg_ms, void* stream);
 
 /* diagnostics: SM-cycle stamps of CTA 0 of the last attention launch (synchronises the device); 32 int64 values:
  * [0] start, [1] K/V landed, [2+4t] S issued, [3+4t] P ready, [4+4t] PV issued (t = query tile 0,1),

@@ -136,3 +136,25 @@ def test_empty_and_degenerate_queries():
     assert (out["scores"][1] == 0).all()
     for k in ("tar_pts", "src_pts", "ransac_scores", "idx_failed"):
         assert torch.equal(out[k][[0, 2]].to(ref[k].dtype), ref[k][[0, 2]]), k
+
+
+@pytest.mark.parametrize("B,O,T", [(5, 2, 10), (3, 3, 1), (32, 8, 162)])
+def test_pair_kernel_is_bit_identical_to_the_one_cta_kernel(B, O, T, monkeypatch):
+    """`sim_search_pair_kernel` (2-CTA clusters, tcgen05 cta_group::2, column maxima exchanged through distributed
+    shared memory) against `sim_search_kernel`: every output of the chain, floats included, must be equal bit for bit
+    (same products, same accumulation order, same summation order of the per-template score)."""
+    case = synth.make_feature_case(B=B, O=O, T=max(T, 5), seed=77 + B)
+    reg = port.RegressorPort(seed=6)
+    outs = []
+    for pair in ("0", "1"):
+        monkeypatch.setenv("GIGAPOSE_SIM_PAIR", pair)
+        eng = engine_from_case(case, regressor=reg)
+        out = cpu(run_engine(eng, case))
+        eng.set_queries(case.q_feat, case.q_mask16.reshape(-1, 16, 16), case.q_label - 1)
+        cand = cpu(eng.sim_candidates())
+        out.update({"cand_" + k: v for k, v in cand.items()})
+        if B <= 8:
+            out["tiles"] = eng.debug_sim_tiles().cpu()
+        outs.append(out)
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
