@@ -47,6 +47,9 @@ WORKLOADS = {
     "c2": dict(O=8, T=162, B=32, desc="LM-O-shaped: 8 objects x 162 templates, batch 32"),
     "c3": dict(O=30, T=162, B=64, desc="T-LESS-shaped: 30 objects x 162 templates, batch 64"),
     "c4": dict(O=21, T=162, B=128, desc="YCB-V-shaped: 21 objects x 162 templates, batch 128"),
+    # BASELINE.json configs[4]: 8 GPUs only (154.6 GB of descriptors); one query per object = no template reuse (B_o = 1)
+    "c5": dict(O=256, T=576, B=256, desc="stress: 256 objects x 576 templates (HANDAL-scale), batch 256, one query per object",
+               one_query_per_object=True),
 }
 DTYPE = ("f32 (a1, a4, a6: bf16 hi/lo split x3 on tensor cores with fp32 accumulate = fp32-faithful; "
          "a5, a7-a9: fp32)")
@@ -121,11 +124,13 @@ class SyntheticTemplates:
         return tc.PandasTensorCollection(infos=pd.DataFrame(), K=self.K, rgb=rgb, mask=mask, M=self.M[o], poses=self.poses)
 
 
-def make_queries(templates: SyntheticTemplates, B, seed=42):
+def make_queries(templates: SyntheticTemplates, B, seed=42, one_per_object=False):
     """B query crops = planted template crops + noise; host-pinned tensors (what the DataLoader hands over)."""
     import src.megapose.utils.tensor_collection as tc
     gc = torch.Generator().manual_seed(seed)
     labels = torch.randint(1, templates.O + 1, (B,), generator=gc)
+    if one_per_object:
+        labels = (torch.arange(B) % templates.O) + 1
     views = torch.randint(0, templates.T, (B,), generator=gc)
     imgs, masks = [], []
     for b in range(B):
@@ -241,65 +246,110 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # CPU reference arm: the oracle port (the reference modules cannot travel to the GPU box) on all host threads
 # ----------------------------------------------------------------------------------------------------------------
-_CPU_THREADS = None
-_CPU_CTX = {}
+class CpuReference:
+    """The reference's PyTorch path restated on the CPU (oracle/port.py: pinned against the unmodified reference by
+    tests/golden), sequenced exactly like `GigaPose.eval_retrieval` (gigaPose.py:497-604), on the box's host cores.
+
+    World: `n_det` detections over `n_obj` objects x T templates (for c2 that IS the full batch: 32 detections, 8 objects;
+    for the larger configurations a bounded sample of the same shape).  Template descriptors / IST features / masks are
+    the planted synthetic bank in the reference's own layout ([O,T,1024,16,16] f32 etc.); query crops go through the
+    ViT-L/14 and IST backbones (their outputs are timed, the downstream stages run on the planted query features of the
+    same shapes so that the matching stage has real structure to work on).
+
+    Variants:  "as_written" = the reference as it stands: per-detection bank gathers
+    `ae_features[label-1]`, `mask[label-1]` (gigaPose.py:520-521) and, inside the k loop, `ist_features[label-1]` plus a
+    fresh IST backbone pass over all crops for each of the k hypotheses (gigaPose.py:552-553);  "fair" = the same
+    arithmetic with the backbone run once and the IST bank gathered once."""
+
+    def __init__(self, T, n_det=32, n_obj=8, k=5):
+        from gigapose_b200 import synth
+        from oracle import port
+        self.port, self.k, self.T = port, k, T
+        gc = torch.Generator().manual_seed(4242)
+        labels = torch.randint(1, n_obj + 1, (n_det,), generator=gc)
+        case = synth.make_feature_case(B=n_det, O=n_obj, T=T, seed=77, labels=labels, obj_chunk=1)
+        O = n_obj
+        # the reference's template_data tensors (gigaPose.py:383-390)
+        self.ae_features = case.bank_feat.permute(0, 1, 3, 2).reshape(O, T, 1024, 16, 16).contiguous()
+        self.masks = synth.mask16_to_224(case.bank_mask16).contiguous()                     # [O,T,224,224]
+        self.ist_features = case.bank_ist
+        self.tar_feat = case.q_feat.permute(0, 2, 1).reshape(n_det, 1024, 16, 16).contiguous()
+        self.tar_mask = synth.mask16_to_224(case.q_mask16)
+        self.tar_ist = case.q_ist
+        self.case = case
+        self.rgb = synth.make_crops(n_det, seed=78)[0]
+        self.vit, self.backbone, self.reg = port.DinoV2Port(), port.ISTBackbonePort(), port.RegressorPort()
+        self.n_det, self.n_obj = n_det, n_obj
+
+    @torch.no_grad()
+    def run(self, variant="fair", n=None):
+        """One pass over the first `n` detections; returns (seconds, per-stage seconds)."""
+        port, k = self.port, self.k
+        n = n or self.n_det
+        c = self.case
+        st = {}
+        t_all = time.perf_counter()
+
+        def tic(name, t0):
+            st[name] = st.get(name, 0.0) + time.perf_counter() - t0
+
+        t0 = time.perf_counter(); _ = port.ae_features(self.vit, self.rgb[:n]); tic("a1_vit", t0)
+        lab = c.q_label[:n] - 1
+        t0 = time.perf_counter()
+        src_feats = self.ae_features[lab]                                        # gigaPose.py:520 (170 MB per detection)
+        src_masks = self.masks[lab]                                              # gigaPose.py:521
+        tic("a3_bank_gather", t0)
+        t0 = time.perf_counter()
+        pred = port.similarity_search(src_feats, self.tar_feat[:n], src_masks, self.tar_mask[:n], k=k)
+        tic("a4_similarity_topk", t0)
+        del src_feats, src_masks
+        rel_scale = torch.zeros(n, k, 256)
+        rel_inpl = torch.zeros(n, k, 256, 2)
+        bi = torch.arange(n)
+        src_ist = None
+        for kk in range(k):                                                      # gigaPose.py:545-575
+            if variant == "as_written" or kk == 0:
+                t0 = time.perf_counter(); src_ist = self.ist_features[lab]; tic("a3_bank_gather", t0)   # :552
+                t0 = time.perf_counter(); _ = self.backbone(self.rgb[:n]); tic("a6_ist_backbone", t0)   # :553
+            t0 = time.perf_counter()
+            rel_scale[:, kk], rel_inpl[:, kk] = port.ist_mlp(self.reg, src_ist[bi, pred["id_src"][:, kk]], self.tar_ist[:n],
+                                                             pred["src_pts"][:, kk], pred["tar_pts"][:, kk])
+            tic("a5_ist_mlp", t0)
+        t0 = time.perf_counter()
+        M, failed, in_src, in_tar, in_sc = port.ransac(pred["src_pts"], pred["tar_pts"], rel_scale, rel_inpl)
+        tic("a7_ransac", t0)
+        t0 = time.perf_counter()
+        scores = torch.sum(in_sc, dim=2) / 256
+        order = torch.argsort(scores, dim=1, descending=True)
+        ids = pred["id_src"][bi[:, None], order]
+        Ms = M[bi[:, None], order]
+        _ = port.pose_recovery(c.q_label[:n], c.q_K[:n], c.q_M[:n], ids, Ms.clone(), c.bank_K, c.bank_M, c.bank_poses)
+        tic("a8_a9_sort_pose", t0)
+        return time.perf_counter() - t_all, st
+
+    def sweep_threads(self, cands, n):
+        """Fastest thread count for the whole chain on the first `n` detections (more threads are not always faster for
+        the reference's many small ops: 128 threads were measured 20x slower than 8 on the RANSAC python loops)."""
+        best, best_t, seen = cands[0], float("inf"), {}
+        for cnum in cands:
+            torch.set_num_threads(cnum)
+            self.run("fair", n=min(2, n))                       # warm the thread pool
+            t, _ = self.run("fair", n=n)
+            seen[cnum] = round(t, 3)
+            if t < best_t:
+                best, best_t = cnum, t
+        torch.set_num_threads(best)
+        return best, seen
 
 
-def _pick_cpu_threads(run_once):
-    """More threads are not always faster for the reference's many small ops (128 threads were measured 20x slower
-    than 8 on this path): time one tiny run at a few thread counts and keep the best."""
-    global _CPU_THREADS
-    if _CPU_THREADS is not None:
-        return _CPU_THREADS
+def cpu_thread_candidates():
     ncpu = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
-    best, best_t = cands[0], float("inf")
-    for c in cands:
-        torch.set_num_threads(c)
-        run_once()                                  # warm
-        t0 = time.perf_counter()
-        run_once()
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = c, dt
-    _CPU_THREADS = best
-    return best
+    return sorted({c for c in (16, 32, 64, ncpu) if c <= ncpu}) or [ncpu]
 
 
-def cpu_reference_rate(cfg, sample_dets=2, reps=1, threads=None):
-    """Times the CPU restatement of the reference path (oracle/port.py, pinned against the unmodified reference by
-    tests/golden) on a bounded sample: `sample_dets` detections of one object against its full T-template bank.
-    Returns detections/s.  Includes a1 (ViT) + a4 + a6 (once, the "fair" variant) + a5 + a7-a9."""
-    from gigapose_b200 import synth
-    from oracle import port
-    T = cfg["T"]
-    key = (T, sample_dets)
-    if key not in _CPU_CTX:                         # models + inputs are built once per process
-        _CPU_CTX.clear()
-        case = synth.make_feature_case(B=sample_dets, O=1, T=T, seed=77)
-        _CPU_CTX[key] = (synth.to_reference_layout(case), port.DinoV2Port(), port.ISTBackbonePort(), port.RegressorPort(),
-                         synth.make_crops(sample_dets, seed=78)[0])
-    ri, vit, backbone, reg, rgb = _CPU_CTX[key]
-
-    def run(n=sample_dets):
-        _ = port.ae_features(vit, rgb[:n])          # a1 on the query crops
-        _ = backbone(rgb[:n])                       # a6 once per crop
-        sub = {k: (v[:n] if k in ("src_feats", "tar_feat", "src_masks", "tar_mask", "src_ist", "tar_ist", "tar_label",
-                                  "tar_K", "tar_M") else v) for k, v in ri.items()}
-        _ = port.retrieval(sub, reg)                # a4, a5, a7, a8, a9 on planted features of the same shape
-
-    threads = threads or _pick_cpu_threads(lambda: run(1))
-    torch.set_num_threads(threads)
-    times = []
-    for _ in range(reps + 1):                       # first repetition = warm-up
-        t0 = time.perf_counter()
-        run()
-        times.append(time.perf_counter() - t0)
-    best = min(times[1:]) if len(times) > 1 else times[0]
-    return sample_dets / best, dict(cores=threads, kind="port",
-                                    sample=f"{sample_dets} detections vs 1 object x {T} templates, fp32 torch CPU "
-                                           f"({threads} of {os.cpu_count()} host threads: fastest of a short sweep), "
-                                           f"ViT-L/14 + IST backbone once + similarity/MLP/RANSAC/pose, best of {reps}")
+def sample_shape(cfg):
+    """Detections / objects of the CPU sample for a workload: the full batch for c1 / c2, a c2-sized slice otherwise."""
+    return min(cfg["B"], 32), min(cfg["O"], 8)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -327,22 +377,41 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl_name = args.workload or {1: "c2", 2: "c2", 4: "c3", 8: "c4"}.get(args.gpus, "c2")
     cfg = WORKLOADS[wl_name]
+    if wl_name == "c5" and args.gpus < 8 and args.impl != "reference":
+        raise SystemExit("workload c5 (154.6 GB of template descriptors) needs --gpus 8")
     config = {"workload": f"{wl_name}: {cfg['desc']}", "objects": cfg["O"], "templates": cfg["T"], "batch": cfg["B"],
               "k": 5, "l2": "inputs larger than L2 (template bank 1.36 GB at c2 vs 126 MB L2); no explicit flush"}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        vals, info = [], None
-        for i in range(min(args.warmup, 1) + args.steps):     # each step = a bounded 2-detection sample (~seconds)
-            v, info = cpu_reference_rate(cfg, sample_dets=2, reps=1)
-            if i >= min(args.warmup, 1):
-                vals.append(v)
+        n_det, n_obj = sample_shape(cfg)
+        ref = CpuReference(cfg["T"], n_det=n_det, n_obj=n_obj)
+        # warm-up steps double as the thread sweep on the FULL sample (one candidate per warm-up step, at least one)
+        cands = cpu_thread_candidates()
+        cands = cands[-max(1, min(len(cands), args.warmup)):]
+        threads, sweep = ref.sweep_threads(cands, n=n_det)
+        vals, stages = [], {}
+        for i in range(args.steps):
+            t, st = ref.run("fair")
+            vals.append(n_det / t)
+            for kname, v in st.items():
+                stages[kname] = stages.get(kname, 0.0) + v / args.steps
+        t_aw, st_aw = ref.run("as_written")
         value = statistics.mean(vals)
+        sample = (f"{n_det} detections over {n_obj} objects x {cfg['T']} templates per step"
+                  + (" (the full batch)" if n_det == cfg["B"] and n_obj == cfg["O"] else f" (bounded sample of B={cfg['B']}, O={cfg['O']})")
+                  + f", fp32 torch on the host CPU, {threads} of {os.cpu_count()} threads (fastest of {sweep} s per step), "
+                    "'fair' variant: ViT-L/14 + bank gathers + similarity / top-k + IST backbone once + MLP + RANSAC + pose")
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * 2 / value, "higher_is_better": True,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_det / value, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": dict(value=value, unit=UNIT, **info),
+                "cpu_baseline": dict(value=value, unit=UNIT, cores=threads, kind="port", sample=sample,
+                                     stage_s={kk: round(v, 4) for kk, v in stages.items()},
+                                     as_written=dict(value=n_det / t_aw, unit=UNIT,
+                                                     stage_s={kk: round(v, 4) for kk, v in st_aw.items()},
+                                                     note="IST backbone and IST bank gather repeated for each of the k=5 "
+                                                          "hypotheses (gigaPose.py:552-553), one pass")),
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         emit(line)
@@ -470,6 +539,25 @@ def main():
                 "note": "algorithmic FLOPs = 2*T*P^2*C per detection; the fp32-faithful mode executes 3 bf16 tensor passes "
                         "per algorithmic FLOP, so frac <= 1/3 by construction"}
 
+    # the kernel that dominates the step (60 % of it): the 96 linear layers of the ViT, timed alone back to back
+    # (96 x iters launches = a long run: the sustained peak is the denominator)
+    roofline_vit = None
+    vit_entry = getattr(model.ae_net.dinov2_model, "_gp_vit_engine", None)
+    if vit_entry is not None:
+        vit_ms = vit_entry[1].time_linears(cfg["B"], iters=5)
+        depth = vit_entry[1].depth
+        vit_flops = cfg["B"] * depth * 2.0 * 257 * 1024 * (3072 + 1024 + 4096 + 4096)
+        peak_sus = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
+        ach = vit_flops / (vit_ms / 1e3) / 1e12
+        roofline_vit = {"bound": "tensor", "kernel": "vit_gemm_kernel<swap=0,pair=1> (qkv, proj, fc1, fc2 of 24 blocks)",
+                        "achieved": ach, "peak": peak_sus, "unit": "TFLOP/s", "frac": ach / peak_sus, "traffic": None,
+                        "launches": 4 * depth, "ms_per_forward": vit_ms, "ms_per_launch": vit_ms / (4 * depth),
+                        "executed_tflops": 3 * ach, "executed_frac_of_peak": 3 * ach / peak_sus,
+                        "share_of_step": vit_ms / ms,
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernels timed in a long back-to-back run)",
+                        "note": "algorithmic FLOPs = 2*M*N*K of the 4 linears x depth (155.2 GFLOP per crop); 3 tensor passes "
+                                "per algorithmic FLOP (fp32-faithful split)"}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": DTYPE,
@@ -478,11 +566,20 @@ def main():
             "clocks": clocks.summary(),
             "e2e": {"value": cfg["B"] / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
-            "gpu_launches": int(launches), "roofline": roofline, "stage_ms": stage_ms}
+            "gpu_launches": int(launches), "roofline": roofline, "roofline_dominant": roofline_vit, "stage_ms": stage_ms}
     line["config"]["cuda_graph"] = bool(model.use_cuda_graph)
     if not args.no_cpu_baseline:
-        v, info = cpu_reference_rate(cfg, sample_dets=4, reps=2)
-        line["cpu_baseline"] = dict(value=v, unit=UNIT, **info)
+        # the CPU restatement of the reference on this box's host cores: thread count from a sweep on 4 detections, then
+        # ONE pass over the bounded sample (the full c2 batch) with per-stage times
+        n_det, n_obj = sample_shape(cfg)
+        ref = CpuReference(cfg["T"], n_det=n_det, n_obj=n_obj)
+        threads, sweep = ref.sweep_threads(cpu_thread_candidates(), n=min(4, n_det))
+        t, st = ref.run("fair")
+        line["cpu_baseline"] = dict(value=n_det / t, unit=UNIT, cores=threads, kind="port",
+                                    sample=f"{n_det} detections over {n_obj} objects x {cfg['T']} templates, one pass of the "
+                                           f"'fair' variant (IST backbone once), fp32 torch, {threads} of {os.cpu_count()} host "
+                                           f"threads (fastest of a 4-detection sweep: {sweep} s)",
+                                    stage_s={kk: round(v, 4) for kk, v in st.items()})
     emit(line)
     return 0
 

@@ -86,10 +86,9 @@ int gp_internal_fail(int code, const char* fmt, ...) {
 }
 void gp_internal_count_launches(int n) { g_launches += n; }
 namespace gp {
-bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* ev = getenv("GIGAPOSE_PDL"); v = ev ? (ev[0] != '0') : 1; }
-  return v != 0;
+bool pdl_enabled() {                      // read at every launch: scripts A/B it inside one process
+  const char* ev = getenv("GIGAPOSE_PDL");
+  return ev ? (ev[0] != '0') : true;
 }
 }  // namespace gp
 
@@ -309,7 +308,7 @@ int gp_create(const gp_config_t* cfg, void* bank_mem, void* workspace_mem, gp_ha
   h->cur_B = 0;
   {
     const char* ev = getenv("GIGAPOSE_SIM_PAIR");
-    h->sim_pair = ev ? (ev[0] != '0') : 0;
+    h->sim_pair = ev ? (ev[0] != '0') : 1;      // default: the 2-CTA cluster kernel (GIGAPOSE_SIM_PAIR=0: 1-CTA kernel)
   }
   h->nccl_comm = nullptr;
   h->rank = 0;

@@ -64,6 +64,44 @@ def weights_fingerprint(*modules) -> str:
     return h.hexdigest()[:16]
 
 
+class _BankBuilder:
+    """Row f2: streams the template crops of consecutive objects through both encoders in FULL chunks (the reference, and
+    round 1 here, encoded one object at a time: 162 crops = 64 + 64 + 34, i.e. a ragged last ViT pass per object) and
+    writes descriptors / sampled masks / IST features straight into the engine's bank in the kernel-native layout
+    (the trunk's patch-major output is stored as is: no transposes on the way)."""
+
+    def __init__(self, model, eng, chunk=64):
+        self.model, self.eng, self.chunk = model, eng, chunk
+        self.rgb, self.mask, self.segs, self.count, self.crops = [], [], [], 0, 0
+
+    def add(self, obj, rgb, mask):
+        T, t0 = rgb.shape[0], 0
+        while t0 < T:
+            take = min(self.chunk - self.count, T - t0)
+            self.rgb.append(rgb[t0:t0 + take])
+            self.mask.append(mask[t0:t0 + take])
+            self.segs.append((obj, t0, take))
+            self.count += take
+            t0 += take
+            if self.count == self.chunk:
+                self.flush()
+
+    def flush(self):
+        if not self.count:
+            return
+        rgb = torch.cat(self.rgb) if len(self.rgb) > 1 else self.rgb[0]
+        mask = torch.cat(self.mask) if len(self.mask) > 1 else self.mask[0]
+        tokens = self.model.ae_net.patch_tokens(rgb)                  # [n,256,1024], normalised once (ae_net.py:69)
+        ist = self.model.ist_net.forward_by_chunk(rgb)                # [n,256,16,16] (channels-last view of patch-major)
+        off = 0
+        for obj, t0, n in self.segs:
+            self.eng.bank_write(obj, t0, tokens[off:off + n], mask[off:off + n], ist_feat=ist[off:off + n],
+                                norm_passes=1)                        # + matching.py:229
+            off += n
+        self.crops += self.count
+        self.rgb, self.mask, self.segs, self.count = [], [], [], 0
+
+
 class GigaPose(LightningModule):
     def __init__(self, model_name, ae_net, ist_net, training_loss, testing_metric, optim_config, log_interval, log_dir,
                  max_num_dets_per_forward=None, test_setting="localization", **kwargs):
@@ -139,16 +177,15 @@ class GigaPose(LightningModule):
                 cached = True
             except GigaPoseNativeError as e:           # other weights / shape / ABI: rebuild and overwrite
                 logger.info(f"bank cache {cache} not usable ({e}); re-encoding the templates")
+        builder = _BankBuilder(self, eng)
         for idx in range(n_obj):
             data = first if idx == 0 else dataset[idx]
             if not cached:
-                rgb = data.rgb.to(device)
-                tokens = self.ae_net.patch_tokens(rgb)                   # [T,256,1024], normalised once (ae_net.py:69)
-                ist = self.ist_net.forward_by_chunk(rgb)                 # [T,256,16,16]
-                eng.bank_write(idx, 0, tokens, data.mask.to(device), ist_feat=ist, norm_passes=1)   # + matching.py:229
+                builder.add(idx, data.rgb.to(device, non_blocking=True), data.mask.to(device, non_blocking=True))
             Ks.append(data.K.to(device))
             Ms.append(data.M.to(device))
             poses.append(data.poses.to(device))
+        builder.flush()
         K, M, P = torch.stack(Ks).float(), torch.stack(Ms).float(), torch.stack(poses).float()
         eng.set_poses(K, M, P)
         eng.set_ist_weights(self.ist_net.regressor)
@@ -159,7 +196,51 @@ class GigaPose(LightningModule):
         self.engines[dataset_name] = eng
         self.template_datas[dataset_name] = tc.PandasTensorCollection(infos=pd.DataFrame(), K=K, M=M, poses=P)
         self.pose_recovery[dataset_name] = ObjectPoseRecovery(template_K=K, template_Ms=M, template_poses=P)
-        logger.info(f"Init {dataset_name} done! Avg time={start.elapsed_time(stop) / 1e3 / n_obj:.3f} s/object")
+        self.onboarding_s_per_object = start.elapsed_time(stop) / 1e3 / n_obj
+        logger.info(f"Init {dataset_name} done! Avg time={self.onboarding_s_per_object:.3f} s/object")
+
+    @torch.no_grad()
+    def onboard_templates(self, dataset_name, rgba, boxes, K, poses):
+        """Row f2, from raw renders: the whole `TemplateSet.__getitem__` + `set_template_data` sequence
+        (dataloader/template.py:55-81 -> gigaPose.py:357-398) on the GPU for all objects at once.
+
+        rgba  [O,T,4,H,W] float in [0,1] (rendered RGB + alpha; uint8 / 255 is fine) or a list of O such tensors,
+        boxes [O,T,4] xyxy template boxes, K [3,3] or [O,3,3] template intrinsics, poses [O,T,4,4].
+        Crop + resize + pad (`CropResizePad`, utils/crop.py:16-61) and the CLIP normalisation of the RGB channels
+        (template.py:71-73) run as one gather kernel per object (`gp_crop_resize_pad`); the crops then stream through the
+        ViT / IST encoders in full 64-crop chunks across object boundaries into the bank."""
+        from gigapose_b200.engine import Engine
+        from gigapose_b200.preprocess import CLIP_MEAN, CLIP_STD, crop_resize_pad
+        device = self.device
+        n_obj = len(rgba)
+        T = rgba[0].shape[0]
+        metric = self.testing_metric
+        eng = Engine(n_obj, T, self.max_dets_per_call, device=device, k=metric.k, sim_threshold=metric.sim_threshold,
+                     patch_threshold=metric.patch_threshold, precision=getattr(metric, "precision", "fp32_split"))
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        builder = _BankBuilder(self, eng)
+        Ms = []
+        for o in range(n_obj):
+            crop = crop_resize_pad(torch.as_tensor(boxes[o]), rgba[o].to(device, non_blocking=True).float(), 224,
+                                   mean=CLIP_MEAN + (0.0,), std=CLIP_STD + (1.0,))      # alpha channel passes through
+            builder.add(o, crop["images"][:, :3], crop["images"][:, 3])
+            Ms.append(crop["M"])
+        builder.flush()
+        K = torch.as_tensor(K, dtype=torch.float32, device=device)
+        K = K.expand(n_obj, 3, 3).contiguous() if K.dim() == 2 else K
+        M = torch.stack(Ms).float()
+        P = torch.as_tensor(poses, dtype=torch.float32, device=device)
+        eng.set_poses(K, M, P)
+        eng.set_ist_weights(self.ist_net.regressor)
+        stop.record()
+        stop.synchronize()
+        self.engines[dataset_name] = eng
+        self.template_datas[dataset_name] = tc.PandasTensorCollection(infos=pd.DataFrame(), K=K, M=M, poses=P)
+        self.pose_recovery[dataset_name] = ObjectPoseRecovery(template_K=K, template_Ms=M, template_poses=P)
+        self.onboarding_s_per_object = start.elapsed_time(stop) / 1e3 / n_obj
+        logger.info(f"Onboarded {dataset_name}: {n_obj} objects x {T} templates, {self.onboarding_s_per_object:.3f} s/object")
+        return eng
 
     # ------------------------------------------------------------------ localisation filter + writer (gigaPose.py:400-449)
     def filter_and_save(self, predictions, test_list, time, save_path, keep_only_testing_instances=True):
@@ -247,9 +328,19 @@ class GigaPose(LightningModule):
         with torch.cuda.stream(self._copy_stream):
             staged = tc.PandasTensorCollection(infos=batch.infos, **{k: v.to(device, non_blocking=True)
                                                                      for k, v in batch._tensors.items()})
-            labels = torch.from_numpy(object_indices(batch.infos, self.engines[dataset_name].O)).pin_memory()
-            staged._q_obj = labels.to(device, non_blocking=True)          # object indices (gigaPose.py:514-520)
-            staged._q_obj_host = labels                                    # keeps the pinned source alive until the copy ran
+            # object indices (gigaPose.py:514-520) through a small ring of pinned buffers: a fresh `pin_memory()` per batch
+            # goes through cudaHostAlloc, which was measured to stall the launching thread for up to 10 ms
+            idx = object_indices(batch.infos, self.engines[dataset_name].O)
+            ring = getattr(self, "_label_ring", None)
+            if ring is None:
+                ring = self._label_ring = {"slot": 0, "bufs": {}}
+            ring["slot"] = (ring["slot"] + 1) % 4
+            key = (ring["slot"], len(idx))
+            labels = ring["bufs"].get(key)
+            if labels is None:
+                labels = ring["bufs"][key] = torch.empty(len(idx), dtype=torch.int64, pin_memory=True)
+            labels.copy_(torch.from_numpy(idx))
+            staged._q_obj = labels.to(device, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(self._copy_stream)
         staged._ready = ready

@@ -128,8 +128,9 @@ def test_crop_level_chain_matches_oracle():
     valid = ref["src_pts"][..., 0] != -1
     d_scale = float((_by_template(out, ref, "relScale") - ref["relScale"]).abs()[valid].max())
     d_inpl = float((_by_template(out, ref, "relInplane") - ref["relInplane"]).abs()[valid].max())
-    report["fp32_split"].update(relScale_err_max=d_scale, relInplane_err_max=d_inpl)
-    assert d_scale < 2e-3 and d_inpl < 2e-3, (d_scale, d_inpl)
+    r_scale = float(ref["relScale"].abs()[valid].max())
+    report["fp32_split"].update(relScale_err_max=d_scale, relScale_abs_max=r_scale, relInplane_err_max=d_inpl)
+    assert d_scale < 1e-3 * max(1.0, r_scale) and d_inpl < 2e-3, (d_scale, r_scale, d_inpl)
     # (3) rows a7 - a9 are exact functions of their inputs: the ORACLE's RANSAC + pose lifting run on the GPU's own
     # (relScale, relInplane) reproduce the GPU's inlier sets bit for bit and its poses to 1e-3
     M_o, failed_o, in_src_o, in_tar_o, in_sc_o = port.ransac(out["src_pts"], out["tar_pts"], out["relScale"], out["relInplane"])

