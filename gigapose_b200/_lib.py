@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "libgigapose_b200.so")
 GP_ABI_VERSION = 2
 LAYOUT_CHANNEL_MAJOR = 0
 LAYOUT_PATCH_MAJOR = 1
+LAYOUT_VIT_TOKENS = 2
 PRECISION_FP32_SPLIT = 0
 PRECISION_BF16 = 1
 
@@ -95,6 +96,7 @@ SYMBOLS = {
     "gp_ist_trunk_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gp_debug_ist_trunk": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "gp_debug_sim_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "gp_normalize_patch_tokens": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gp_vit_time_linears": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
     "gp_time_sim_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
 }

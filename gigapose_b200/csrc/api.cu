@@ -334,6 +334,36 @@ int gp_destroy(gp_handle_t h) {
   return GP_OK;
 }
 
+namespace {
+// descriptor rows of one of the three accepted layouts -> normalised bf16 hi/lo planes (k-block-tiled)
+int split_features(const float* feat, int feat_layout, long long n_imgs, int norm_passes, uint16_t* hi, uint16_t* lo, cudaStream_t s) {
+  const long long rows = n_imgs * GP_NUM_PATCHES;
+  cudaError_t e;
+  if (feat_layout == GP_LAYOUT_CHANNEL_MAJOR)
+    e = gp::launch_split_descriptors(feat, rows, GP_AE_DIM, GP_NUM_PATCHES, (long long)GP_NUM_PATCHES * GP_AE_DIM, 1, GP_NUM_PATCHES,
+                                     norm_passes, 1, hi, lo, nullptr, s);
+  else if (feat_layout == GP_LAYOUT_PATCH_MAJOR)
+    e = gp::launch_split_descriptors(feat, rows, GP_AE_DIM, GP_NUM_PATCHES, (long long)GP_NUM_PATCHES * GP_AE_DIM, GP_AE_DIM, 1,
+                                     norm_passes, 1, hi, lo, nullptr, s);
+  else if (feat_layout == GP_LAYOUT_VIT_TOKENS)     // [n,257,C]: token 0 (CLS) of every crop is skipped
+    e = gp::launch_split_descriptors(feat + GP_AE_DIM, rows, GP_AE_DIM, GP_NUM_PATCHES, (long long)(GP_NUM_PATCHES + 1) * GP_AE_DIM,
+                                     GP_AE_DIM, 1, norm_passes, 1, hi, lo, nullptr, s);
+  else
+    return fail(GP_ERR_INVALID, "unknown feature layout %d", feat_layout);
+  if (e != cudaSuccess) return fail(GP_ERR_CUDA, "descriptor split failed: %s", cudaGetErrorString(e));
+  return GP_OK;
+}
+}  // namespace
+
+int gp_normalize_patch_tokens(int b, const float* x_prenorm, float* out, void* stream) {
+  if (!x_prenorm || !out || b < 1) return fail(GP_ERR_INVALID, "bad argument");
+  GP_CUDA(gp::launch_split_descriptors(x_prenorm + GP_AE_DIM, (long long)b * GP_NUM_PATCHES, GP_AE_DIM, GP_NUM_PATCHES,
+                                       (long long)(GP_NUM_PATCHES + 1) * GP_AE_DIM, GP_AE_DIM, 1, 1, 0, nullptr, nullptr, out,
+                                       static_cast<cudaStream_t>(stream)));
+  g_launches += 1;
+  return GP_OK;
+}
+
 int gp_bank_write(gp_handle_t h, int obj, int tmpl0, int n, const float* feat, int feat_layout, int norm_passes,
                   const float* mask, int H, int W, const float* ist_feat, void* stream) {
   if (!h) return fail(GP_ERR_INVALID, "null handle");
@@ -346,17 +376,8 @@ int gp_bank_write(gp_handle_t h, int obj, int tmpl0, int n, const float* feat, i
   if (norm_passes < 0 || norm_passes > 2) return fail(GP_ERR_INVALID, "norm_passes must be 0, 1 or 2");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t slot = (size_t)obj * c.num_templates + tmpl0;
-  const long long rows = (long long)n * GP_NUM_PATCHES;
   const size_t plane_off = slot * GP_NUM_PATCHES * GP_AE_DIM;
-  const long long img_stride = (long long)GP_NUM_PATCHES * GP_AE_DIM;
-  if (feat_layout == GP_LAYOUT_CHANNEL_MAJOR)
-    GP_CUDA(gp::launch_split_descriptors(feat, rows, GP_AE_DIM, GP_NUM_PATCHES, img_stride, 1, GP_NUM_PATCHES, norm_passes, 1,
-                                         h->bank.hi + plane_off, h->bank.lo + plane_off, nullptr, s));
-  else if (feat_layout == GP_LAYOUT_PATCH_MAJOR)
-    GP_CUDA(gp::launch_split_descriptors(feat, rows, GP_AE_DIM, GP_NUM_PATCHES, img_stride, GP_AE_DIM, 1, norm_passes, 1,
-                                         h->bank.hi + plane_off, h->bank.lo + plane_off, nullptr, s));
-  else
-    return fail(GP_ERR_INVALID, "unknown feature layout %d", feat_layout);
+  if (int e = split_features(feat, feat_layout, n, norm_passes, h->bank.hi + plane_off, h->bank.lo + plane_off, s)) return e;
   GP_CUDA(gp::launch_sample_mask16(mask, n, H, W, h->bank.mask16 + slot * GP_NUM_PATCHES, s));
   g_launches += 2;
   if (ist_feat) {
@@ -417,16 +438,7 @@ int gp_set_queries(gp_handle_t h, int B, const float* q_feat, int feat_layout, i
   if (H < 16 || W < 16) return fail(GP_ERR_INVALID, "mask must be at least 16x16");
   if (norm_passes < 0 || norm_passes > 2) return fail(GP_ERR_INVALID, "norm_passes must be 0, 1 or 2");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const long long rows = (long long)B * GP_NUM_PATCHES;
-  const long long img_stride = (long long)GP_NUM_PATCHES * GP_AE_DIM;
-  if (feat_layout == GP_LAYOUT_CHANNEL_MAJOR)
-    GP_CUDA(gp::launch_split_descriptors(q_feat, rows, GP_AE_DIM, GP_NUM_PATCHES, img_stride, 1, GP_NUM_PATCHES, norm_passes, 1,
-                                         h->ws.q_hi, h->ws.q_lo, nullptr, s));
-  else if (feat_layout == GP_LAYOUT_PATCH_MAJOR)
-    GP_CUDA(gp::launch_split_descriptors(q_feat, rows, GP_AE_DIM, GP_NUM_PATCHES, img_stride, GP_AE_DIM, 1, norm_passes, 1,
-                                         h->ws.q_hi, h->ws.q_lo, nullptr, s));
-  else
-    return fail(GP_ERR_INVALID, "unknown feature layout %d", feat_layout);
+  if (int e = split_features(q_feat, feat_layout, B, norm_passes, h->ws.q_hi, h->ws.q_lo, s)) return e;
   GP_CUDA(gp::launch_sample_mask16(q_mask, B, H, W, h->ws.q_mask16, s));
   // object ids are clamped into [0, O) on the way in: an out-of-range label must not turn into an out-of-bounds bank
   // address (the host-side callers validate and raise; see GigaPose.retrieve)

@@ -61,8 +61,7 @@ split_descriptors_kernel(const float* __restrict__ x, long long n_rows, int C, i
       // per K-block is one contiguous 16 KB slab (streams from HBM at full page locality when nothing is shared)
       const size_t o = tiled ? ((((size_t)(r / rows_per_img) * (C / 32) + (c >> 5)) * rows_per_img + (r % rows_per_img)) << 5) + (c & 31)
                              : (size_t)r * C + c;
-      hi[o] = h;
-      lo[o] = l;
+      if (hi) { hi[o] = h; lo[o] = l; }
       if (normalized_out) normalized_out[r * C + c] = v[i];
     }
   }

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 from ._lib import (GpCandidates, GpConfig, GpMatches, GpPredictions, GpRansacOut, LAYOUT_CHANNEL_MAJOR,
-                   LAYOUT_PATCH_MAJOR, PRECISION_BF16, PRECISION_FP32_SPLIT, check)
+                   LAYOUT_PATCH_MAJOR, LAYOUT_VIT_TOKENS, PRECISION_BF16, PRECISION_FP32_SPLIT, check)
 
 P = 256
 C_AE = 1024
@@ -39,6 +39,8 @@ def _feature_layout(feat: torch.Tensor):
         if feat.stride() == (P * c, 1, w * c, c):          # [n,16,16,C] memory viewed as [n,C,16,16]
             return feat, LAYOUT_PATCH_MAJOR
         return feat.contiguous(), LAYOUT_CHANNEL_MAJOR
+    if feat.dim() == 3 and feat.shape[1] == P + 1:         # raw ViT tokens [n,257,C] (`x_prenorm`): CLS row skipped in-kernel
+        return feat.contiguous(), LAYOUT_VIT_TOKENS
     assert feat.dim() == 3 and feat.shape[1] == P, f"bad descriptor shape {tuple(feat.shape)}"
     return feat.contiguous(), LAYOUT_PATCH_MAJOR
 
@@ -124,7 +126,8 @@ class Engine:
     # ---------------------------------------------------------------------------------------------- onboarding
     def bank_write(self, obj: int, tmpl0: int, feat: torch.Tensor, mask: torch.Tensor,
                    ist_feat: Optional[torch.Tensor] = None, norm_passes: int = 1) -> None:
-        """feat: [n,1024,16,16] or [n,256,1024]; mask: [n,H,W]; ist_feat: [n,256,16,16] (optional)."""
+        """feat: [n,1024,16,16], [n,256,1024] or raw ViT tokens [n,257,1024] (use norm_passes=2); mask: [n,H,W];
+        ist_feat: [n,256,16,16] (optional)."""
         feat, layout = _feature_layout(_f32(feat, self.device))
         mask = _f32(mask, self.device).contiguous()
         n = feat.shape[0]

@@ -44,6 +44,8 @@ typedef struct gp_context* gp_handle_t;
 /* feature layouts accepted by gp_bank_write / gp_set_queries */
 #define GP_LAYOUT_CHANNEL_MAJOR 0   /* [n, C, 16, 16]  -- what the reference modules exchange (ae_net.py:49-53) */
 #define GP_LAYOUT_PATCH_MAJOR 1     /* [n, 256, C]     -- ViT token order, kernel-native                       */
+#define GP_LAYOUT_VIT_TOKENS 2      /* [n, 257, C]     -- raw `x_prenorm` of gp_vit_forward: the CLS row of every crop is
+                                       skipped (ae_net.py:65); use norm_passes = 2 (ae_net.py:69 + matching.py:229)   */
 
 /* precision of the similarity contraction */
 #define GP_PRECISION_FP32_SPLIT 0   /* bf16 hi/lo planes, hi*hi + hi*lo + lo*hi on tcgen05: fp32-faithful indices */
@@ -219,6 +221,11 @@ int gp_vit_destroy(gp_vit_handle_t h);
 /* img f32 [b,3,224,224] -> x_prenorm f32 [b,257,1024]: tokens after the last block, before the final norm
  * (DinoVisionTransformer.forward_features()["x_prenorm"], the tensor ae_net.py:65 slices). */
 int gp_vit_forward(gp_vit_handle_t h, int b, const float* img, float* x_prenorm, void* stream);
+
+/* AENet.forward_by_chunk's tail (ae_net.py:65-69): drops the CLS row of x_prenorm [b,257,1024] and L2-normalises every
+ * patch token (F.normalize semantics) -> out f32 [b,256,1024] (patch-major; its channels-last view is the [b,1024,16,16]
+ * tensor the reference module returns).  Needs no handle. */
+int gp_normalize_patch_tokens(int b, const float* x_prenorm, float* out, void* stream);
 
 /* --- rows a6 / f1: IST trunk (ResNet, resnet.py:318-381 called at ist_net.py:62-63), BatchNorm folded ------------ */
 #define GP_IST_TRUNK_NUM_CONVS 21

@@ -91,12 +91,12 @@ class _BankBuilder:
             return
         rgb = torch.cat(self.rgb) if len(self.rgb) > 1 else self.rgb[0]
         mask = torch.cat(self.mask) if len(self.mask) > 1 else self.mask[0]
-        tokens = self.model.ae_net.patch_tokens(rgb)                  # [n,256,1024], normalised once (ae_net.py:69)
+        tokens = self.model.ae_net.raw_tokens(rgb)                    # [n,257,1024] x_prenorm; CLS drop + both normalisations in-kernel
         ist = self.model.ist_net.forward_by_chunk(rgb)                # [n,256,16,16] (channels-last view of patch-major)
         off = 0
         for obj, t0, n in self.segs:
             self.eng.bank_write(obj, t0, tokens[off:off + n], mask[off:off + n], ist_feat=ist[off:off + n],
-                                norm_passes=1)                        # + matching.py:229
+                                norm_passes=2)                        # ae_net.py:69 + matching.py:229
             off += n
         self.crops += self.count
         self.rgb, self.mask, self.segs, self.count = [], [], [], 0
@@ -276,9 +276,9 @@ class GigaPose(LightningModule):
         """Rows a1, a3-a9 for at most `eng.max_batch` detections; every step is a kernel launch on the current
         stream, no host synchronisation -> capturable as a CUDA graph."""
         mark("start")
-        tokens = self.ae_net.patch_tokens(tar_img)
+        tokens = self.ae_net.raw_tokens(tar_img)                             # x_prenorm [b,257,1024]
         mark("a1_vit")
-        eng.set_queries(tokens, tar_mask, q_obj, norm_passes=1)
+        eng.set_queries(tokens, tar_mask, q_obj, norm_passes=2)              # CLS drop, ae_net.py:69, matching.py:229 fused
         m = eng.sim_topk()
         mark("a3_a4_similarity_topk")
         tar_ist = self.ist_net.forward_by_chunk(tar_img)                     # once, not k times

@@ -7,7 +7,6 @@ view of a patch-major `[b,256,1024]` buffer: identical values/shape for any call
 it without a transpose.
 """
 import torch
-import torch.nn.functional as F
 
 from src.models._lightning import LightningModule
 from src.utils.logging import get_logger
@@ -31,16 +30,25 @@ class AENet(LightningModule):
         return self.dinov2_model.parameters()
 
     @torch.no_grad()
-    def patch_tokens(self, images: torch.Tensor) -> torch.Tensor:
-        """[b,3,H,W] -> L2-normalised patch-major tokens [b, h*w, C] (ae_net.py:55-69)."""
+    def raw_tokens(self, images: torch.Tensor) -> torch.Tensor:
+        """[b,3,224,224] -> `x_prenorm` [b,257,1024] (CLS + patch tokens before the final norm, un-normalised): what the
+        resident-bank path hands to `gp_set_queries` / `gp_bank_write` (layout GP_LAYOUT_VIT_TOKENS, norm_passes=2), so
+        that the CLS drop and both L2 normalisations (ae_net.py:65-69, matching.py:229) fuse into the plane split."""
         from gigapose_b200.vit_engine import vit_forward_features
-        outs = []
-        for i in range(0, images.shape[0], self.max_batch_size):
-            tok = vit_forward_features(self.dinov2_model, images[i:i + self.max_batch_size],
-                                       precision=getattr(self, "precision", None))[:, 1:, :]
-            outs.append(tok)
-        tok = torch.cat(outs, 0) if len(outs) > 1 else outs[0]
-        return F.normalize(tok, dim=2)
+        outs = [vit_forward_features(self.dinov2_model, images[i:i + self.max_batch_size], precision=getattr(self, "precision", None))
+                for i in range(0, images.shape[0], self.max_batch_size)]
+        return torch.cat(outs, 0) if len(outs) > 1 else outs[0]
+
+    @torch.no_grad()
+    def patch_tokens(self, images: torch.Tensor) -> torch.Tensor:
+        """[b,3,H,W] -> L2-normalised patch-major tokens [b, h*w, C] (ae_net.py:55-69), normalised by the library
+        (`gp_normalize_patch_tokens`), not by ATen."""
+        from gigapose_b200 import _lib
+        tok = self.raw_tokens(images)
+        out = torch.empty(tok.shape[0], tok.shape[1] - 1, tok.shape[2], device=tok.device)
+        _lib.check(_lib.load().gp_normalize_patch_tokens(tok.shape[0], tok.data_ptr(), out.data_ptr(),
+                                                         torch.cuda.current_stream(tok.device).cuda_stream))
+        return out
 
     def forward_by_chunk(self, processed_rgbs, patch_dim=(2, 3)):
         gh = processed_rgbs.shape[patch_dim[0]] // self.patch_size

@@ -244,8 +244,8 @@ def test_bank_persistence_round_trip(tmp_path):
     model2.template_datasets = {"synthetic": templates}
     model2.test_dataset_name = "synthetic"
     calls = {"n": 0}
-    orig = model2.ae_net.patch_tokens
-    model2.ae_net.patch_tokens = lambda x: (calls.__setitem__("n", calls["n"] + x.shape[0]), orig(x))[1]
+    orig = model2.ae_net.raw_tokens
+    model2.ae_net.raw_tokens = lambda x: (calls.__setitem__("n", calls["n"] + x.shape[0]), orig(x))[1]
     second = model2.retrieve(batch, "synthetic")
     assert calls["n"] == 4                                  # only the 4 query crops went through the ViT
     for name in ("id_src", "pred_poses", "scores"):
