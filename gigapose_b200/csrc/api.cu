@@ -86,9 +86,12 @@ int gp_internal_fail(int code, const char* fmt, ...) {
 }
 void gp_internal_count_launches(int n) { g_launches += n; }
 namespace gp {
-bool pdl_enabled() {                      // read at every launch: scripts A/B it inside one process
+// Off by default: a same-process A/B (scripts/pdl_ab.py, profiles/r02_pdl_ab.md) measured no gain on the ViT chain --
+// the persistent 1-CTA-per-SM kernels hold all shared memory / TMEM until they exit, so a dependent grid cannot become
+// resident early enough to hide anything but its own ~2 us prologue.  GIGAPOSE_PDL=1 turns it on (read at every launch).
+bool pdl_enabled() {
   const char* ev = getenv("GIGAPOSE_PDL");
-  return ev ? (ev[0] != '0') : true;
+  return ev ? (ev[0] != '0') : false;
 }
 }  // namespace gp
 

@@ -1,6 +1,9 @@
 // Multi-head self-attention of the ViT-L/14 forward on TMA + tcgen05 (row a1; 257 tokens, 16 heads x 64).
 //
-// One CTA per (crop, head).  K and V of the head (272 key rows: 257 + padding) are TMA-staged once into shared
+// Persistent CTAs (one per SM) walk the (crop, head) items; the TMA producer runs ahead of the tensor pipe, so the next
+// item's Q / K / V tiles land while the current item's softmax and P.V still run (K and Q are free as soon as the last
+// S = Q K^T of an item has retired), and barrier setup / TMEM allocation / cold instruction fetch are paid once per SM
+// instead of once per item.  Per item: K and V of the head (272 key rows: 257 + padding) are TMA-staged once into shared
 // memory as bf16 hi/lo planes (SWIZZLE_128B, 128-byte rows); the 257 query rows go through in three 128-row tiles:
 //   S = Q K^T          tcgen05.mma SS, M=128, N=256+16, K=64      (A = Q tile, B = K, both K-major)   -> TMEM [0,272)
 //   softmax            256 threads, two per query row (keys [0,128) and [128,257); the two warps of a TMEM lane quarter
@@ -37,7 +40,7 @@ constexpr uint32_t kIdescS16 = umma_idesc_f16(128, 16, 1);
 constexpr uint32_t kIdescPV = umma_idesc_f16(128, 64, 1, /*B MN-major*/ 1);
 
 struct __align__(8) AttnTail {
-  uint64_t k_full, v_full, q_full[2], q_empty[2], s_full, p_ready, o_full;
+  uint64_t k_full, v_full, k_empty, v_empty, q_full[2], q_empty[2], s_full, p_ready, o_full;
   uint32_t tmem_base;
 };
 constexpr int kSmem = 1024 + 4 * kKVPlane + 4 * kQPlane + sizeof(AttnTail);
@@ -75,7 +78,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_constant__ CUtensorMap tm_lo_128,
                     const __grid_constant__ CUtensorMap tm_hi_16, const __grid_constant__ CUtensorMap tm_lo_16,
                     const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __restrict__ qkv_lo,
-                    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int crop_stride, int passes) {
+                    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int crop_stride, int passes,
+                    int num_items) {
   extern __shared__ uint8_t smem_raw[];
   pdl_trigger();
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -84,16 +88,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
   uint8_t* sQ = smem + 4 * kKVPlane;                                          // [buf][hi|lo]
   AttnTail& tail = *reinterpret_cast<AttnTail*>(smem + 4 * kKVPlane + 4 * kQPlane);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int img = blockIdx.x / kHeads, head = blockIdx.x % kHeads;
-  const int row0 = img * kTok;                       // first token row of this crop in the [M, 1024] output planes
-  // head-major operand planes [q|k|v][crop][head][token][64]: first row of this (crop, head) in each section
-  const int rq = ((0 * crop_stride + img) * kHeads + head) * kTok;
-  const int rk = ((1 * crop_stride + img) * kHeads + head) * kTok;
-  const int rv = ((2 * crop_stride + img) * kHeads + head) * kTok;
+  // item -> (crop, head) and the first rows of its operands: head-major planes [q|k|v][crop][head][token][64]
+  auto coords = [&](int item, int& head, int& row0, int& rq, int& rk, int& rv) {
+    const int img = item / kHeads;
+    head = item % kHeads;
+    row0 = img * kTok;                               // first token row of this crop in the [M, 1024] output planes
+    rq = ((0 * crop_stride + img) * kHeads + head) * kTok;
+    rk = ((1 * crop_stride + img) * kHeads + head) * kTok;
+    rv = ((2 * crop_stride + img) * kHeads + head) * kTok;
+  };
 
   if (threadIdx.x == 0) {
     mbar_init(&tail.k_full, 1);
     mbar_init(&tail.v_full, 1);
+    mbar_init(&tail.k_empty, 2);                       // last S = Q K^T retired (tcgen05.commit) + the token-256 warp is done with K
+    mbar_init(&tail.v_empty, 2);                       // last P V retired + the token-256 warp is done with V
     for (int i = 0; i < 2; ++i) { mbar_init(&tail.q_full[i], 1); mbar_init(&tail.q_empty[i], 1); }
     mbar_init(&tail.s_full, 1);
     mbar_init(&tail.p_ready, kSoftmaxWarps);
@@ -114,44 +123,58 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
       const int np = passes == 3 ? 2 : 1;
       tma_prefetch_desc(&tm_hi_128); tma_prefetch_desc(&tm_hi_16);
       if (np == 2) { tma_prefetch_desc(&tm_lo_128); tma_prefetch_desc(&tm_lo_16); }
-      // order of issue = order of need: Q tile 0, K (for S), then V (only needed after the first softmax)
-      mbar_arrive_expect_tx(&tail.q_full[0], (uint32_t)(np * kQPlane));
-      tma_load_2d(sQ, &tm_hi_128, &tail.q_full[0], 0, rq);
-      if (np == 2) tma_load_2d(sQ + kQPlane, &tm_lo_128, &tail.q_full[0], 0, rq);
-      mbar_arrive_expect_tx(&tail.k_full, (uint32_t)(np * kKVPlane));
-      for (int pl = 0; pl < np; ++pl) {
-        const CUtensorMap* m128 = pl ? &tm_lo_128 : &tm_hi_128;
-        const CUtensorMap* m16 = pl ? &tm_lo_16 : &tm_hi_16;
-        tma_load_2d(sK[pl], m128, &tail.k_full, 0, rk);
-        tma_load_2d(sK[pl] + 128 * kRow, m128, &tail.k_full, 0, rk + 128);
-        tma_load_2d(sK[pl] + 256 * kRow, m16, &tail.k_full, 0, rk + 256);
-      }
-      mbar_arrive_expect_tx(&tail.v_full, (uint32_t)(np * kKVPlane));
-      for (int pl = 0; pl < np; ++pl) {
-        const CUtensorMap* m128 = pl ? &tm_lo_128 : &tm_hi_128;
-        const CUtensorMap* m16 = pl ? &tm_lo_16 : &tm_hi_16;
-        tma_load_2d(sV[pl], m128, &tail.v_full, 0, rv);
-        tma_load_2d(sV[pl] + 128 * kRow, m128, &tail.v_full, 0, rv + 128);
-        tma_load_2d(sV[pl] + 256 * kRow, m16, &tail.v_full, 0, rv + 256);
-      }
-      for (int qt = 1; qt < kQTiles; ++qt) {
-        const int buf = qt & 1;
-        mbar_wait(&tail.q_empty[buf], ((qt >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&tail.q_full[buf], (uint32_t)(np * kQPlane));
-        tma_load_2d(sQ + (buf * 2 + 0) * kQPlane, &tm_hi_128, &tail.q_full[buf], 0, rq + qt * 128);
-        if (np == 2) tma_load_2d(sQ + (buf * 2 + 1) * kQPlane, &tm_lo_128, &tail.q_full[buf], 0, rq + qt * 128);
+      // order of issue = order of need: Q tile 0, K (for S), then V (only needed after the first softmax), Q tile 1.
+      // Every buffer is filled once per item; fill number `it` waits for release number `it - 1` (parity (it & 1) ^ 1,
+      // which a fresh barrier passes at once).
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        int head, row0, rq, rk, rv;
+        coords(item, head, row0, rq, rk, rv);
+        const uint32_t free_par = (uint32_t)(it & 1) ^ 1u;
+        mbar_wait(&tail.q_empty[0], free_par);
+        mbar_arrive_expect_tx(&tail.q_full[0], (uint32_t)(np * kQPlane));
+        tma_load_2d(sQ, &tm_hi_128, &tail.q_full[0], 0, rq);
+        if (np == 2) tma_load_2d(sQ + kQPlane, &tm_lo_128, &tail.q_full[0], 0, rq);
+        mbar_wait(&tail.k_empty, free_par);
+        mbar_arrive_expect_tx(&tail.k_full, (uint32_t)(np * kKVPlane));
+        for (int pl = 0; pl < np; ++pl) {
+          const CUtensorMap* m128 = pl ? &tm_lo_128 : &tm_hi_128;
+          const CUtensorMap* m16 = pl ? &tm_lo_16 : &tm_hi_16;
+          tma_load_2d(sK[pl], m128, &tail.k_full, 0, rk);
+          tma_load_2d(sK[pl] + 128 * kRow, m128, &tail.k_full, 0, rk + 128);
+          tma_load_2d(sK[pl] + 256 * kRow, m16, &tail.k_full, 0, rk + 256);
+        }
+        mbar_wait(&tail.v_empty, free_par);
+        mbar_arrive_expect_tx(&tail.v_full, (uint32_t)(np * kKVPlane));
+        for (int pl = 0; pl < np; ++pl) {
+          const CUtensorMap* m128 = pl ? &tm_lo_128 : &tm_hi_128;
+          const CUtensorMap* m16 = pl ? &tm_lo_16 : &tm_hi_16;
+          tma_load_2d(sV[pl], m128, &tail.v_full, 0, rv);
+          tma_load_2d(sV[pl] + 128 * kRow, m128, &tail.v_full, 0, rv + 128);
+          tma_load_2d(sV[pl] + 256 * kRow, m16, &tail.v_full, 0, rv + 256);
+        }
+        for (int qt = 1; qt < kQTiles; ++qt) {
+          const int buf = qt & 1;
+          mbar_wait(&tail.q_empty[buf], free_par);
+          mbar_arrive_expect_tx(&tail.q_full[buf], (uint32_t)(np * kQPlane));
+          tma_load_2d(sQ + (buf * 2 + 0) * kQPlane, &tm_hi_128, &tail.q_full[buf], 0, rq + qt * 128);
+          if (np == 2) tma_load_2d(sQ + (buf * 2 + 1) * kQPlane, &tm_lo_128, &tail.q_full[buf], 0, rq + qt * 128);
+        }
       }
     }
   } else if (warp == 1) {
     // ============================== UMMA issuer ==============================
     if (lane == 0) {
-      mbar_wait(&tail.k_full, 0);
+      const uint32_t kh = smem_u32(sK[0]), kl = smem_u32(sK[1]), vh = smem_u32(sV[0]), vl = smem_u32(sV[1]);
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const uint32_t item_par = (uint32_t)(it & 1);      // K, V and each Q buffer are filled once per item
+      mbar_wait(&tail.k_full, item_par);
       tc_fence_after();
       STAMP(1);
-      const uint32_t kh = smem_u32(sK[0]), kl = smem_u32(sK[1]), vh = smem_u32(sV[0]), vl = smem_u32(sV[1]);
       for (int qt = 0; qt < kQTiles; ++qt) {
         const int buf = qt & 1;
-        mbar_wait(&tail.q_full[buf], (qt >> 1) & 1);
+        mbar_wait(&tail.q_full[buf], item_par);
         tc_fence_after();
         const uint32_t qh = smem_u32(sQ + (buf * 2 + 0) * kQPlane), ql = smem_u32(sQ + (buf * 2 + 1) * kQPlane);
         // S = Q K^T : keys [0,256) and [256,272)
@@ -169,10 +192,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
           }
         }
         umma_commit(&tail.q_empty[buf]);               // Q buffer free once these MMAs retire
+        if (qt == kQTiles - 1) umma_commit(&tail.k_empty);   // ... and K: the producer may fetch the next item's keys
         umma_commit(&tail.s_full);
         STAMP(2 + 4 * qt);
         // O = P V once the softmax warps have written P
-        if (qt == 0) mbar_wait(&tail.v_full, 0);
+        if (qt == 0) mbar_wait(&tail.v_full, item_par);
         mbar_wait(&tail.p_ready, qt & 1);
         tc_fence_after();
         STAMP(3 + 4 * qt);
@@ -187,7 +211,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
           }
         }
         umma_commit(&tail.o_full);
+        if (qt == kQTiles - 1) umma_commit(&tail.v_empty);
         STAMP(4 + 4 * qt);
+      }
       }
     }
   } else if (warp < 2 + kSoftmaxWarps) {
@@ -200,6 +226,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
     const int r = quarter * 32 + lane;                 // query row inside the tile
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const uint32_t s_base = tmem + lane_base + kColS + 128 * half;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    int head, row0, rq_, rk_, rv_;
+    coords(item, head, row0, rq_, rk_, rv_);
+    // s_full / p_ready / o_full complete twice per item, so their parity is the q-tile index whatever the item
     for (int qt = 0; qt < kQTiles; ++qt) {
       const int tok = qt * 128 + r;
       const bool row_ok = tok < kTok;
@@ -305,10 +335,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
       tc_fence_before();                               // O / S reads done before the next tile's MMAs overwrite them
       if (warp == 2 && lane == 0) STAMP(16 + 5 * qt);
     }
+    }
   } else {
     // ============================== token 256 on one warp (fp32 FMAs from the smem planes) ==============================
     __shared__ float s_p[kKeys];
     __shared__ float s_q[kHd];
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+    int head, row0, rq, rk_, rv_;
+    coords(item, head, row0, rq, rk_, rv_);
+    const uint32_t item_par = (uint32_t)(it & 1);
+    __syncwarp();                                      // the previous item's reads of s_q / s_p are done
     // q (64 values): lane loads q[2*lane], q[2*lane+1] straight from the planes and shares them through smem
     const size_t qoff = (size_t)(rq + 256) * kHd + 2 * lane;
     const uint32_t qh = *reinterpret_cast<const uint32_t*>(qkv_hi + qoff);
@@ -316,7 +353,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
     s_q[2 * lane] = __uint_as_float(qh << 16) + __uint_as_float(ql << 16);
     s_q[2 * lane + 1] = __uint_as_float(qh & 0xffff0000u) + __uint_as_float(ql & 0xffff0000u);
     __syncwarp();
-    mbar_wait(&tail.k_full, 0);
+    mbar_wait(&tail.k_full, item_par);
     if (lane == 0) STAMP(24);
     const uint8_t* klo = passes == 3 ? sK[1] : nullptr;   // bf16 mode: the lo planes are not loaded
     const uint8_t* vlo = passes == 3 ? sV[1] : nullptr;
@@ -359,8 +396,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
     __syncwarp();
-    if (lane == 0) STAMP(25);
-    mbar_wait(&tail.v_full, 0);
+    if (lane == 0) { STAMP(25); mbar_arrive(&tail.k_empty); }   // every lane's K reads precede the shuffles above
+    mbar_wait(&tail.v_full, item_par);
     // output: lane handles d = 2*lane, 2*lane+1 (4 partial accumulators, loads batched by the unroll)
     float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 8
@@ -382,7 +419,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_
     const size_t oo = (size_t)(row0 + 256) * kDim + head * kHd + 2 * lane;
     *reinterpret_cast<uint32_t*>(out_hi + oo) = h;
     *reinterpret_cast<uint32_t*>(out_lo + oo) = l;
-    if (lane == 0) STAMP(26);
+    __syncwarp();                                      // every lane's V reads are done
+    if (lane == 0) { STAMP(26); mbar_arrive(&tail.v_empty); }
+    }
   }
 
   tc_fence_before();
@@ -407,9 +446,16 @@ cudaError_t launch_attention_tc(const CUtensorMap& hi128, const CUtensorMap& lo1
     configured = true;
   }
   if (b <= 0) return cudaSuccess;
-  return launch_ex(attention_tc_kernel, dim3(b * kHeads), dim3(kThreads), kSmem, s, 1, true, hi128, lo128, hi16, lo16,
-                   reinterpret_cast<const __nv_bfloat16*>(qkv_hi), reinterpret_cast<const __nv_bfloat16*>(qkv_lo),
-                   reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), crop_stride, passes);
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int items = b * kHeads;
+  return launch_ex(attention_tc_kernel, dim3(items < num_sms ? items : num_sms), dim3(kThreads), kSmem, s, 1, true, hi128, lo128,
+                   hi16, lo16, reinterpret_cast<const __nv_bfloat16*>(qkv_hi), reinterpret_cast<const __nv_bfloat16*>(qkv_lo),
+                   reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), crop_stride, passes, items);
 }
 
 }  // namespace gp

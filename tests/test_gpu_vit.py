@@ -54,3 +54,19 @@ def test_native_vit_bf16_mode_is_close():
     got = NativeViT(mine, DEV, max_crops=2, precision="bf16").forward(rgb.to(DEV)).cpu()
     rel = ((got - want).norm() / want.norm()).item()
     assert rel < 2e-2, rel
+
+
+def test_persistent_attention_over_many_crops_is_batch_invariant():
+    """20 crops = 320 (crop, head) items on 148 persistent attention CTAs: every CTA loops over 2-3 items with the next
+    item's Q / K / V prefetched behind the current one.  The result of a crop must not depend on what else is in the batch
+    (bit-identical to a 2-crop call) and must match the oracle."""
+    ref, mine = _pair(2, seed=11)
+    rgb, _ = synth.make_crops(20, seed=13)
+    eng = NativeViT(mine, DEV, max_crops=32)
+    big = eng.forward(rgb.to(DEV)).cpu()
+    for i in (0, 9, 18):
+        small = eng.forward(rgb[i:i + 2].to(DEV)).cpu()
+        assert torch.equal(big[i:i + 2], small), i
+    want = ref.forward_features(rgb[:6])["x_prenorm"]
+    err = (big[:6] - want).abs().max().item()
+    assert err < 3e-4 * max(1.0, want.abs().max().item()), err

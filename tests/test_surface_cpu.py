@@ -113,3 +113,41 @@ def test_ist_trunk_weight_folding_matches_eval_mode_modules():
     other = ResNet(dict(n_heads=0, input_dim=3, input_size=256, initial_dim=64, block_dims=[64, 128, 256, 512],
                         descriptor_size=256))
     assert not ist_trunk.supports(other)                                   # other geometries stay on the torch path
+
+
+def test_labels_outside_the_bank_raise():
+    """ADVICE r1: the reference indexes `ae_features[label - 1]` -- label 0 wraps to the last object, label > O raises;
+    here both raise before anything reaches the kernels."""
+    import pandas as pd
+    import pytest
+    from src.models.gigaPose import object_indices
+    assert object_indices(pd.DataFrame(dict(label=["1", "3", "2"])), 3).tolist() == [0, 2, 1]
+    for bad in (["0", "1"], ["4"], ["-1"]):
+        with pytest.raises(IndexError):
+            object_indices(pd.DataFrame(dict(label=bad)), 3)
+
+
+def test_bank_cache_fingerprint_follows_the_weights():
+    import torch
+    from src.models.gigaPose import weights_fingerprint
+    a, b = torch.nn.Linear(8, 8), torch.nn.BatchNorm1d(8)
+    f0 = weights_fingerprint(a, b)
+    assert f0 == weights_fingerprint(a, b)
+    with torch.no_grad():
+        a.weight[3, 3] += 1e-3
+    assert weights_fingerprint(a, b) != f0
+    b.running_var[0] = 2.0
+    assert weights_fingerprint(a, b) != f0
+
+
+def test_detection_windows_and_light_records():
+    from gigapose_b200 import multigpu
+    assert [multigpu.window(5, r, 2) for r in range(2)] == [(0, 3), (3, 5)]
+    assert [multigpu.window(3, r, 4) for r in range(4)] == [(0, 1), (1, 2), (2, 3), (3, 3)]
+    covered = sorted(i for r in range(8) for i in range(*multigpu.window(128, r, 8)))
+    assert covered == list(range(128))
+    full, n_full = multigpu.record_layout(4, 5)
+    light, n_light = multigpu.record_layout(4, 5, light=True)
+    assert set(light) == set(multigpu.LIGHT_FIELDS) and "rel_scale" in full and n_light < n_full
+    assert n_light == 4 * 5 * (4 + 4 + 256 * 4 + 256 + 256)            # 1544 B per candidate, no padding needed here
+    assert all(off % 16 == 0 for off, _, _ in light.values())
