@@ -60,7 +60,7 @@ SYMBOLS = {
                                 C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "gp_bank_write_ist": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "gp_bank_set_poses": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "gp_set_ist_weights": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int]),
+    "gp_set_ist_weights": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     "gp_set_queries": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p]),
     "gp_sim_candidates": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GpCandidates), C.c_void_p]),

@@ -19,6 +19,7 @@ int gp_internal_make_map_raw(CUtensorMap* map, void* ptr, int rank, const uint64
                              const uint32_t* box, const uint32_t* elem_strides);
 int gp_internal_make_map_ex(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows,
                             int swizzle_bytes);
+int gp_internal_make_map(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
 
 namespace {
 
@@ -171,8 +172,11 @@ struct Workspace {
   uint8_t *rec_idx, *rec_valid;
   // local candidates
   float* c_score; int* c_id; float* c_pts_score; uint8_t *c_idx, *c_valid;
-  // IST MLP scratch
+  // IST MLP scratch (hidden1 / hidden2 double as the bf16 planes / per-head fp32 rows of the tensor-core form)
   int* row_count; int* row_ids; float *hidden1, *hidden2;
+  uint16_t *mlp_a_hi, *mlp_a_lo;                       // gathered inputs [Bm*k*256, 512] as bf16 hi / lo planes
+  uint16_t *w1_hi, *w1_lo, *w2s_hi, *w2s_lo, *w2i_hi, *w2i_lo;   // packed regressor weights ([1024,512], [256,512] x 2)
+  float* bias1;                                        // [1024] = scale b1 | inplane b1
 };
 
 void carve_bank(Carver& c, const gp_config_t& cfg, Bank* b) {
@@ -211,6 +215,15 @@ void carve_workspace(Carver& c, const gp_config_t& cfg, Workspace* w) {
   tmp.row_ids = c.take<int>(Bm * k * GP_NUM_PATCHES);
   tmp.hidden1 = c.take<float>(Bm * k * GP_NUM_PATCHES * 1024);
   tmp.hidden2 = c.take<float>(Bm * k * GP_NUM_PATCHES * 512);
+  tmp.mlp_a_hi = c.take<uint16_t>(Bm * k * GP_NUM_PATCHES * 512);
+  tmp.mlp_a_lo = c.take<uint16_t>(Bm * k * GP_NUM_PATCHES * 512);
+  tmp.w1_hi = c.take<uint16_t>(1024 * 512);
+  tmp.w1_lo = c.take<uint16_t>(1024 * 512);
+  tmp.w2s_hi = c.take<uint16_t>(256 * 512);
+  tmp.w2s_lo = c.take<uint16_t>(256 * 512);
+  tmp.w2i_hi = c.take<uint16_t>(256 * 512);
+  tmp.w2i_lo = c.take<uint16_t>(256 * 512);
+  tmp.bias1 = c.take<float>(1024);
   if (w) *w = tmp;
 }
 
@@ -242,6 +255,10 @@ struct gp_context {
   CUtensorMap tm_q_hi, tm_q_lo, tm_t_hi, tm_t_lo;
   CUtensorMap tm_t_hi128, tm_t_lo128;   // 128-row boxes: each CTA of a pair stages half of a template slab
   int sim_pair;      // similarity kernel on 2-CTA clusters (GIGAPOSE_SIM_PAIR, default on)
+  int mlp_tc;        // IST MLP hidden layers on tcgen05 (GIGAPOSE_MLP_SIMT=1 selects the fp32 SIMT kernels)
+  CUtensorMap tm_ma_hi, tm_ma_lo;                 // MLP layer 1: gathered rows [rows,512]
+  CUtensorMap tm_h1s_hi, tm_h1s_lo, tm_h1i_hi, tm_h1i_lo;   // layer 2: column halves of hidden1 [rows,1024]
+  CUtensorMap tm_w1_hi, tm_w1_lo, tm_w2s_hi, tm_w2s_lo, tm_w2i_hi, tm_w2i_lo;
   gp::IstMlpWeights mlp;
   bool mlp_set;
   int cur_B;      // batch size staged by gp_set_queries (0 = none)
@@ -310,6 +327,10 @@ int gp_create(const gp_config_t* cfg, void* bank_mem, void* workspace_mem, gp_ha
   h->mlp_set = false;
   h->cur_B = 0;
   {
+    const char* ev = getenv("GIGAPOSE_MLP_SIMT");
+    h->mlp_tc = ev ? (ev[0] == '0') : 1;
+  }
+  {
     const char* ev = getenv("GIGAPOSE_SIM_PAIR");
     h->sim_pair = ev ? (ev[0] != '0') : 1;      // default: the 2-CTA cluster kernel (GIGAPOSE_SIM_PAIR=0: 1-CTA kernel)
   }
@@ -327,6 +348,25 @@ int gp_create(const gp_config_t* cfg, void* bank_mem, void* workspace_mem, gp_ha
       (e = make_plane_map(&h->tm_q_hi, h->ws.q_hi, q_rows, 128)) || (e = make_plane_map(&h->tm_q_lo, h->ws.q_lo, q_rows, 128))) {
     delete h;
     return e;
+  }
+  {
+    const uint64_t rows = (uint64_t)cfg->max_batch * cfg->top_k * GP_NUM_PATCHES;
+    uint16_t* h1_hi = reinterpret_cast<uint16_t*>(h->ws.hidden1);
+    uint16_t* h1_lo = h1_hi + rows * 1024;
+    const uint64_t dims[2] = {512, rows}, strides[1] = {1024 * sizeof(uint16_t)};
+    const uint32_t box[2] = {32, 128}, estr[2] = {1, 1};
+    int e;
+    if ((e = gp_internal_make_map(&h->tm_ma_hi, h->ws.mlp_a_hi, rows, 512, 128)) || (e = gp_internal_make_map(&h->tm_ma_lo, h->ws.mlp_a_lo, rows, 512, 128)) ||
+        (e = gp_internal_make_map_raw(&h->tm_h1s_hi, h1_hi, 2, dims, strides, box, estr)) ||
+        (e = gp_internal_make_map_raw(&h->tm_h1s_lo, h1_lo, 2, dims, strides, box, estr)) ||
+        (e = gp_internal_make_map_raw(&h->tm_h1i_hi, h1_hi + 512, 2, dims, strides, box, estr)) ||
+        (e = gp_internal_make_map_raw(&h->tm_h1i_lo, h1_lo + 512, 2, dims, strides, box, estr)) ||
+        (e = gp_internal_make_map(&h->tm_w1_hi, h->ws.w1_hi, 1024, 512, 128)) || (e = gp_internal_make_map(&h->tm_w1_lo, h->ws.w1_lo, 1024, 512, 128)) ||
+        (e = gp_internal_make_map(&h->tm_w2s_hi, h->ws.w2s_hi, 256, 512, 128)) || (e = gp_internal_make_map(&h->tm_w2s_lo, h->ws.w2s_lo, 256, 512, 128)) ||
+        (e = gp_internal_make_map(&h->tm_w2i_hi, h->ws.w2i_hi, 256, 512, 128)) || (e = gp_internal_make_map(&h->tm_w2i_lo, h->ws.w2i_lo, 256, 512, 128))) {
+      delete h;
+      return e;
+    }
   }
   *out = h;
   return GP_OK;
@@ -422,7 +462,7 @@ int gp_bank_set_poses(gp_handle_t h, const float* K, const float* M, const float
   return GP_OK;
 }
 
-int gp_set_ist_weights(gp_handle_t h, const float* const w[12], int use_tanh) {
+int gp_set_ist_weights(gp_handle_t h, const float* const w[12], int use_tanh, void* stream) {
   if (!h || !w) return fail(GP_ERR_INVALID, "null argument");
   for (int i = 0; i < 12; ++i)
     if (!w[i]) return fail(GP_ERR_INVALID, "IST weight pointer %d is null", i);
@@ -430,6 +470,16 @@ int gp_set_ist_weights(gp_handle_t h, const float* const w[12], int use_tanh) {
   m.s_w1 = w[0]; m.s_b1 = w[1]; m.s_w2 = w[2]; m.s_b2 = w[3]; m.s_w3 = w[4]; m.s_b3 = w[5];
   m.i_w1 = w[6]; m.i_b1 = w[7]; m.i_w2 = w[8]; m.i_b2 = w[9]; m.i_w3 = w[10]; m.i_b3 = w[11];
   m.use_tanh = use_tanh;
+  // tensor-core form: both heads' first layers side by side as one [1024,512] operand, bf16 hi / lo planes
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Workspace& ws = h->ws;
+  GP_CUDA(gp::launch_split_planes(w[0], 512, 512, 512, ws.w1_hi, ws.w1_lo, s));
+  GP_CUDA(gp::launch_split_planes(w[6], 512, 512, 512, ws.w1_hi + 512 * 512, ws.w1_lo + 512 * 512, s));
+  GP_CUDA(gp::launch_split_planes(w[2], 256, 512, 512, ws.w2s_hi, ws.w2s_lo, s));
+  GP_CUDA(gp::launch_split_planes(w[8], 256, 512, 512, ws.w2i_hi, ws.w2i_lo, s));
+  GP_CUDA(cudaMemcpyAsync(ws.bias1, w[1], 512 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  GP_CUDA(cudaMemcpyAsync(ws.bias1 + 512, w[7], 512 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  g_launches += 4;
   h->mlp_set = true;
   return GP_OK;
 }
@@ -544,8 +594,31 @@ int gp_ist_mlp(gp_handle_t h, int b0, int n, const float* q_ist, int ist_layout,
   p.q_obj = h->ws.q_obj + b0; p.q_ist = q_pm; p.bank_ist = h->bank.ist;
   p.rel_scale = rel_scale; p.rel_inplane = rel_inplane;
   p.row_count = h->ws.row_count; p.row_ids = h->ws.row_ids; p.hidden1 = h->ws.hidden1; p.hidden2 = h->ws.hidden2;
-  GP_CUDA(gp::launch_ist_mlp(h->mlp, p, s));
-  g_launches += 4;
+  if (!h->mlp_tc) {
+    GP_CUDA(gp::launch_ist_mlp(h->mlp, p, s));
+    g_launches += 4;
+    return GP_OK;
+  }
+  // tensor-core form: dense rows (row = flat (b,k,t), zeros where invalid) -> 512 -> [512 | 512] -> 256 + 256 -> heads
+  const int rows = n * c.top_k * GP_NUM_PATCHES;                      // a multiple of 256: whole pair tiles
+  const uint64_t max_rows = (uint64_t)c.max_batch * c.top_k * GP_NUM_PATCHES;
+  uint16_t* h1_hi = reinterpret_cast<uint16_t*>(h->ws.hidden1);
+  uint16_t* h1_lo = h1_hi + max_rows * 1024;
+  float* h2s = h->ws.hidden2;
+  float* h2i = h->ws.hidden2 + max_rows * 256;
+  GP_CUDA(gp::launch_mlp_gather_planes(p, h->ws.mlp_a_hi, h->ws.mlp_a_lo, s));
+  gp::GemmParams g{};
+  g.passes = 3; g.pair = 1;
+  g.M = rows; g.N = 1024; g.K = 512; g.mode = gp::GEMM_PLANES_RELU; g.bias = h->ws.bias1; g.out_hi = h1_hi; g.out_lo = h1_lo;
+  GP_CUDA(gp::launch_vit_gemm(h->tm_ma_hi, h->tm_ma_lo, h->tm_w1_hi, h->tm_w1_lo, g, h->num_sms, s));
+  g = gp::GemmParams{};
+  g.passes = 3; g.pair = 1;
+  g.M = rows; g.N = 256; g.K = 512; g.mode = gp::GEMM_ROWS_F32_RELU; g.bias = h->mlp.s_b2; g.x = h2s;
+  GP_CUDA(gp::launch_vit_gemm(h->tm_h1s_hi, h->tm_h1s_lo, h->tm_w2s_hi, h->tm_w2s_lo, g, h->num_sms, s));
+  g.bias = h->mlp.i_b2; g.x = h2i;
+  GP_CUDA(gp::launch_vit_gemm(h->tm_h1i_hi, h->tm_h1i_lo, h->tm_w2i_hi, h->tm_w2i_lo, g, h->num_sms, s));
+  GP_CUDA(gp::launch_mlp_head_rows(h->mlp, p, h2s, h2i, s));
+  g_launches += 5;
   return GP_OK;
 }
 

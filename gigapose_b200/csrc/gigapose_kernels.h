@@ -129,6 +129,13 @@ struct IstMlpParams {
   float* hidden2;             // [B*k*256, 512]
 };
 cudaError_t launch_ist_mlp(const IstMlpWeights& w, const IstMlpParams& p, cudaStream_t stream);
+// Tensor-core form of the two hidden layers (vit_gemm_kernel on bf16 hi/lo planes, fp32-faithful 3-pass products):
+//  * gather: row (b,k,t) = cat(query IST descriptor at tar_pt, template IST descriptor at src_pt) -> planes [B*k*256, 512]
+//    (zeros for invalid correspondences: no compaction, the row index IS the flat (b,k,t) index);
+//  * head: scale = h2_s . w3 + b ; (cos, sin) = tanh(h2_i . W3 + b) in fp32, -1000 where invalid (ist_net.py:110-113).
+cudaError_t launch_mlp_gather_planes(const IstMlpParams& p, uint16_t* a_hi, uint16_t* a_lo, cudaStream_t stream);
+cudaError_t launch_mlp_head_rows(const IstMlpWeights& w, const IstMlpParams& p, const float* h2_scale, const float* h2_inplane,
+                                 cudaStream_t stream);
 
 // ---------------------------------------------------------------- RANSAC + scoring + pose lifting (ransac_pose.cu)
 struct RansacParams {
@@ -180,7 +187,7 @@ cudaError_t launch_pose_only(int n, int k, int T, const int* q_obj, const float*
 
 // ---------------------------------------------------------------- ViT-L/14 (vit_gemm.cu, vit_ops.cu)
 enum GemmMode { GEMM_PLANES = 0, GEMM_PLANES_GELU = 1, GEMM_SCALE_RESIDUAL = 2, GEMM_PATCH_EMBED = 3, GEMM_QKV_HEADS = 4,
-                GEMM_PLANES_RELU = 5, GEMM_PLANES_ADD_RELU = 6, GEMM_ROWS_F32 = 7 };
+                GEMM_PLANES_RELU = 5, GEMM_PLANES_ADD_RELU = 6, GEMM_ROWS_F32 = 7, GEMM_ROWS_F32_RELU = 8 };
 struct GemmParams {
   int M, N, K;                // C[M,N] = A[M,K] W[N,K]^T ; N % 256 == 0, K % 32 == 0
   int passes;                 // 3 = hi*hi + hi*lo + lo*hi, 1 = hi*hi

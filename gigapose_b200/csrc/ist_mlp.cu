@@ -8,6 +8,7 @@
 // fp32 SIMT GEMMs with the gather fused into the A-tile loader: the downstream RANSAC inlier test (<= 14 px) is a
 // knife edge on these outputs, so this stage stays in fp32 rather than on bf16 tensor cores.
 #include "gigapose_kernels.h"
+#include <cuda_bf16.h>
 
 namespace gp {
 
@@ -162,7 +163,99 @@ mlp_head_kernel(IstMlpParams p, IstMlpWeights w, int max_rows) {
   }
 }
 
+// ---- tensor-core form: gather into bf16 hi/lo planes (one warp per correspondence slot) --------------------------------
+__global__ void __launch_bounds__(256)
+mlp_gather_planes_kernel(IstMlpParams p, __nv_bfloat16* __restrict__ a_hi, __nv_bfloat16* __restrict__ a_lo, int total) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= total) return;
+  const long long sx = p.src_pts[2 * (size_t)row], sy = p.src_pts[2 * (size_t)row + 1];
+  const bool valid = (sx != -1) && (sy != -1);
+  const float* q = nullptr;
+  const float* t = nullptr;
+  if (valid) {
+    const int bk = row >> 8, b = bk / p.k;
+    const long long tx = p.tar_pts[2 * (size_t)row], ty = p.tar_pts[2 * (size_t)row + 1];
+    const long long lid = (p.id_src[bk] - p.id_offset) / p.id_stride;
+    q = p.q_ist + ((long long)b * kP + (ty * 16 + tx)) * kIstC;
+    t = p.bank_ist + (((long long)p.q_obj[b] * p.T + lid) * kP + (sy * 16 + sx)) * kIstC;
+  }
+#pragma unroll
+  for (int part = 0; part < 2; ++part) {                  // columns [0,256) = query descriptor, [256,512) = template descriptor
+    const float* src = part ? t : q;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      float4 v = valid ? *reinterpret_cast<const float4*>(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float x[4] = {v.x, v.y, v.z, v.w};
+      __nv_bfloat16 h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { h[j] = __float2bfloat16_rn(x[j]); l[j] = __float2bfloat16_rn(x[j] - __bfloat162float(h[j])); }
+      const size_t o = (size_t)row * 512 + part * 256 + c;
+      *reinterpret_cast<uint2*>(a_hi + o) = make_uint2((uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16),
+                                                       (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16));
+      *reinterpret_cast<uint2*>(a_lo + o) = make_uint2((uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16),
+                                                       (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16));
+    }
+  }
+}
+
+// last layers on dense rows (row = flat (b,k,t)): one warp per row, fp32
+__global__ void __launch_bounds__(256)
+mlp_head_rows_kernel(IstMlpParams p, IstMlpWeights w, const float* __restrict__ h2s, const float* __restrict__ h2i, int total) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= total) return;
+  const bool valid = p.src_pts[2 * (size_t)row] != -1 && p.src_pts[2 * (size_t)row + 1] != -1;
+  float s = 0.f, c0 = 0.f, c1 = 0.f;
+  if (valid) {
+    const float* hs = h2s + (size_t)row * 256;
+    const float* hi = h2i + (size_t)row * 256;
+    for (int i = lane; i < 256; i += 32) {
+      s = fmaf(hs[i], w.s_w3[i], s);
+      const float v = hi[i];
+      c0 = fmaf(v, w.i_w3[i], c0);
+      c1 = fmaf(v, w.i_w3[256 + i], c1);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    c0 += __shfl_xor_sync(0xffffffffu, c0, off);
+    c1 += __shfl_xor_sync(0xffffffffu, c1, off);
+  }
+  if (lane == 0) {
+    if (valid) {
+      s += w.s_b3[0];
+      c0 += w.i_b3[0];
+      c1 += w.i_b3[1];
+      if (w.use_tanh) { c0 = tanhf(c0); c1 = tanhf(c1); }
+    } else {
+      s = c0 = c1 = -1000.0f;                               // ist_net.py:110-113
+    }
+    p.rel_scale[row] = s;
+    p.rel_inplane[2 * (size_t)row] = c0;
+    p.rel_inplane[2 * (size_t)row + 1] = c1;
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_mlp_gather_planes(const IstMlpParams& p, uint16_t* a_hi, uint16_t* a_lo, cudaStream_t stream) {
+  const int total = p.B * p.k * kP;
+  if (total <= 0) return cudaSuccess;
+  mlp_gather_planes_kernel<<<(total + 7) / 8, 256, 0, stream>>>(p, reinterpret_cast<__nv_bfloat16*>(a_hi),
+                                                               reinterpret_cast<__nv_bfloat16*>(a_lo), total);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mlp_head_rows(const IstMlpWeights& w, const IstMlpParams& p, const float* h2_scale, const float* h2_inplane,
+                                 cudaStream_t stream) {
+  const int total = p.B * p.k * kP;
+  if (total <= 0) return cudaSuccess;
+  mlp_head_rows_kernel<<<(total + 7) / 8, 256, 0, stream>>>(p, w, h2_scale, h2_inplane, total);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_ist_mlp(const IstMlpWeights& w, const IstMlpParams& p, cudaStream_t stream) {
   const int total = p.B * p.k * kP;

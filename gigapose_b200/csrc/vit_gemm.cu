@@ -377,13 +377,14 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
               w[j] = __float_as_uint(__uint_as_float(w[j]) + sg[c0 + half * 16 + j] * v[half * 16 + j]);
             store_rows_64B(w, reinterpret_cast<uint8_t*>(p.x), rowb + half * 64);
           }
-        } else if (p.mode == GEMM_ROWS_F32) {             // plain fp32 rows (final 1x1 convolution of the IST trunk)
-          const size_t rowb = (out_row * p.N + n) * 4;
+        } else if (p.mode == GEMM_ROWS_F32 || p.mode == GEMM_ROWS_F32_RELU) {   // plain fp32 rows (last 1x1 convolution of the IST
+          const size_t rowb = (out_row * p.N + n) * 4;                          // trunk; second hidden layer of the IST MLP)
+          const float floor_v = p.mode == GEMM_ROWS_F32_RELU ? 0.f : -INFINITY;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t w[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(v[half * 16 + j]);
+            for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(fmaxf(v[half * 16 + j], floor_v));
             store_rows_64B(w, reinterpret_cast<uint8_t*>(p.x), rowb + half * 64);
           }
         } else {                                          // GEMM_PATCH_EMBED

@@ -215,7 +215,7 @@ class Engine:
         self._keep = ws
         arr = (C.c_void_p * 12)(*[w.data_ptr() for w in ws])
         use_tanh = 1 if isinstance(regressor.inplane_predictor[-1], torch.nn.Tanh) else 0
-        check(self.lib.gp_set_ist_weights(self._h, arr, use_tanh))
+        check(self.lib.gp_set_ist_weights(self._h, arr, use_tanh, self.stream))
 
     # ------------------------------------------------------------------------------------------------ per batch
     def set_queries(self, q_feat: torch.Tensor, q_mask: torch.Tensor, q_obj: torch.Tensor, norm_passes: int = 1) -> None:

@@ -64,8 +64,8 @@ def assert_chain_equal(out, ref, sel=None, pose_tol=1e-3, tag=""):
         assert torch.equal(got.to(ref[k].dtype), ref[k]), f"{tag}{k}: {(got.to(ref[k].dtype) != ref[k]).sum().item()} entries differ"
     assert torch.allclose(pick(out["score_src"]), ref["score_src"], atol=2e-6), tag + "score_src"
     assert torch.allclose(pick(out["score_pts"]), ref["score_pts"], atol=5e-6), tag + "score_pts"
-    assert torch.allclose(pick(out["relScale"]), ref["relScale"], atol=5e-5, rtol=1e-5), tag + "relScale"
-    assert torch.allclose(pick(out["relInplane"]), ref["relInplane"], atol=5e-5, rtol=1e-5), tag + "relInplane"
+    assert torch.allclose(pick(out["relScale"]), ref["relScale"], atol=1e-4, rtol=1e-5), tag + "relScale"
+    assert torch.allclose(pick(out["relInplane"]), ref["relInplane"], atol=1e-4, rtol=1e-5), tag + "relInplane"
     assert torch.allclose(pick(out["M"]), ref["M"], atol=2e-3, rtol=1e-5), tag + "M"
     assert torch.equal(pick(out["scores"]), ref["scores"]), tag + "scores"
     err = (pick(out["pred_poses"]) - ref["pred_poses"]).abs()

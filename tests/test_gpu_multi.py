@@ -39,7 +39,7 @@ def test_two_shards_merge_to_single_bank_result(T, G):
     for key in ("id_src", "tar_pts", "src_pts", "ransac_scores", "ransac_src_pts"):
         assert torch.equal(out[key], ref[key]), key
     assert torch.equal(out["idx_failed"], ref["idx_failed"])
-    assert torch.allclose(out["relScale"], ref["relScale"], atol=2e-5, rtol=1e-5)
+    assert torch.allclose(out["relScale"], ref["relScale"], atol=1e-4, rtol=1e-5)
     err = (out["pred_poses"] - ref["pred_poses"]).abs()
     err[..., :3, 3] /= ref["pred_poses"][..., :3, 3].abs().clamp(min=1.0)
     assert float(err.max()) < 1e-3
@@ -83,7 +83,7 @@ def test_query_sharded_tail_with_replicated_ist_bank(T, G, B):
         out = cpu(eng.sort_and_pose(case.q_K[lo:hi], case.q_M[lo:hi], mw, rs, ri, rr, b0=lo))
         for key in ("id_src", "tar_pts", "src_pts", "ransac_scores", "ransac_src_pts", "idx_failed"):
             assert torch.equal(out[key], ref[key][lo:hi]), (r, key)
-        assert torch.allclose(out["relScale"], ref["relScale"][lo:hi], atol=2e-5, rtol=1e-5)
+        assert torch.allclose(out["relScale"], ref["relScale"][lo:hi], atol=1e-4, rtol=1e-5)
         err = (out["pred_poses"] - ref["pred_poses"][lo:hi]).abs()
         err[..., :3, 3] /= ref["pred_poses"][lo:hi][..., :3, 3].abs().clamp(min=1.0)
         assert float(err.max()) < 1e-3

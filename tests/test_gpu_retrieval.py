@@ -108,8 +108,8 @@ def test_stagewise_against_oracle():
     for kk in range(K):
         rs_ref[:, kk], ri_ref[:, kk] = port.ist_mlp(reg, ri["src_ist"][bi, sim["id_src"][:, kk]], ri["tar_ist"],
                                                    sim["src_pts"][:, kk], sim["tar_pts"][:, kk])
-    assert torch.allclose(rs.cpu(), rs_ref, atol=2e-5, rtol=1e-5)
-    assert torch.allclose(ri_.cpu(), ri_ref, atol=2e-5, rtol=1e-5)
+    assert torch.allclose(rs.cpu(), rs_ref, atol=1e-4, rtol=1e-5)
+    assert torch.allclose(ri_.cpu(), ri_ref, atol=1e-4, rtol=1e-5)
     # a7 on the oracle's MLP outputs
     r = eng.ransac(m_ref, rs_ref.to(dev), ri_ref.to(dev))
     M, failed, in_src, in_tar, in_sc = port.ransac(sim["src_pts"], sim["tar_pts"], rs_ref, ri_ref)
@@ -166,3 +166,24 @@ def test_pair_kernel_equals_the_one_cta_kernel(B, O, T, monkeypatch):
             assert torch.allclose(a[finite], b[finite], atol=tol, rtol=1e-5), (k, float((a[finite] - b[finite]).abs().max()))
         else:
             assert torch.equal(a, b), k
+
+
+def test_tensor_core_mlp_keeps_every_integer_output(monkeypatch):
+    """Row a5 on tcgen05 (split-bf16 x3 hidden layers through vit_gemm_kernel, fp32 heads; the default) against the fp32
+    SIMT kernels (GIGAPOSE_MLP_SIMT=1) on the c2-sized planted case: regressor outputs agree to 1e-4 and every integer
+    output downstream (inlier sets, failure flags, the re-sort) is unchanged."""
+    case = synth.make_feature_case(B=32, O=8, T=162, seed=42)
+    reg = port.RegressorPort(seed=9)
+    outs = []
+    for simt in ("1", "0"):
+        monkeypatch.setenv("GIGAPOSE_MLP_SIMT", simt)
+        eng = engine_from_case(case, regressor=reg)
+        outs.append(cpu(run_engine(eng, case)))
+    a, b = outs
+    valid = a["src_pts"][..., 0] != -1
+    assert torch.equal(a["relScale"] == -1000, b["relScale"] == -1000)
+    d = max(float((a["relScale"] - b["relScale"])[valid].abs().max()), float((a["relInplane"] - b["relInplane"])[valid].abs().max()))
+    assert d < 1e-4, d
+    for k in INT_KEYS:
+        assert torch.equal(a[k], b[k]), k
+    assert torch.equal(a["scores"], b["scores"])

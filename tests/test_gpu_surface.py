@@ -54,7 +54,7 @@ def test_istnet_inference_and_pose_recovery_modules():
         a, b = ist.inference(src_feat=src_ist.to(DEV), tar_feat=ri["tar_ist"].to(DEV),
                              src_pts=sim["src_pts"][:, kk].to(DEV), tar_pts=sim["tar_pts"][:, kk].to(DEV))
         ra, rb = port.ist_mlp(reg_ref, src_ist, ri["tar_ist"], sim["src_pts"][:, kk], sim["tar_pts"][:, kk])
-        assert torch.allclose(a.cpu(), ra, atol=2e-5, rtol=1e-5) and torch.allclose(b.cpu(), rb, atol=2e-5, rtol=1e-5)
+        assert torch.allclose(a.cpu(), ra, atol=1e-4, rtol=1e-5) and torch.allclose(b.cpu(), rb, atol=1e-4, rtol=1e-5)
         rel_scale[:, kk], rel_inpl[:, kk] = ra, rb
     # ObjectPoseRecovery: forward_ransac on a collection, then forward_recovery
     rec = ObjectPoseRecovery(template_K=ri["template_K"].to(DEV), template_Ms=ri["template_Ms"].to(DEV),
