@@ -362,6 +362,8 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch the per-batch kernel sequence eagerly")
+    ap.add_argument("--multi-gpu-graph", action="store_true",
+                    help="N > 1: replay each rank's step (kernels + the two in-library NCCL all-gathers) as one CUDA graph")
     ap.add_argument("--profile-range", action="store_true",
                     help="wrap ONE extra resident step in cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -422,7 +424,8 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=device)
+        from datetime import timedelta
+        dist.init_process_group("nccl", device_id=device, timeout=timedelta(seconds=180))   # a stuck rank fails, not hangs
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     if world > 1:

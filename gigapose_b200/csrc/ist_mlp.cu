@@ -9,6 +9,7 @@
 // knife edge on these outputs, so this stage stays in fp32 rather than on bf16 tensor cores.
 #include "gigapose_kernels.h"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace gp {
 
@@ -165,7 +166,7 @@ mlp_head_kernel(IstMlpParams p, IstMlpWeights w, int max_rows) {
 
 // ---- tensor-core form: gather into bf16 hi/lo planes (one warp per correspondence slot) --------------------------------
 __global__ void __launch_bounds__(256)
-mlp_gather_planes_kernel(IstMlpParams p, __nv_bfloat16* __restrict__ a_hi, __nv_bfloat16* __restrict__ a_lo, int total) {
+mlp_gather_planes_kernel(IstMlpParams p, __half* __restrict__ a_hi, __half* __restrict__ a_lo, int total) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= total) return;
@@ -188,14 +189,15 @@ mlp_gather_planes_kernel(IstMlpParams p, __nv_bfloat16* __restrict__ a_hi, __nv_
       const int c = (lane + 32 * i) * 4;
       float4 v = valid ? *reinterpret_cast<const float4*>(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       const float x[4] = {v.x, v.y, v.z, v.w};
-      __nv_bfloat16 h[4], l[4];
+      // IEEE fp16 hi / lo: 22 significant bits for these O(1) descriptors (bf16 pairs carry 16), same tensor rate
+      __half h[4], l[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { h[j] = __float2bfloat16_rn(x[j]); l[j] = __float2bfloat16_rn(x[j] - __bfloat162float(h[j])); }
+      for (int j = 0; j < 4; ++j) { h[j] = __float2half_rn(x[j]); l[j] = __float2half_rn(x[j] - __half2float(h[j])); }
       const size_t o = (size_t)row * 512 + part * 256 + c;
-      *reinterpret_cast<uint2*>(a_hi + o) = make_uint2((uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16),
-                                                       (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16));
-      *reinterpret_cast<uint2*>(a_lo + o) = make_uint2((uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16),
-                                                       (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16));
+      *reinterpret_cast<uint2*>(a_hi + o) = make_uint2((uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
+                                                       (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
+      *reinterpret_cast<uint2*>(a_lo + o) = make_uint2((uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
+                                                       (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
     }
   }
 }
@@ -244,8 +246,8 @@ mlp_head_rows_kernel(IstMlpParams p, IstMlpWeights w, const float* __restrict__ 
 cudaError_t launch_mlp_gather_planes(const IstMlpParams& p, uint16_t* a_hi, uint16_t* a_lo, cudaStream_t stream) {
   const int total = p.B * p.k * kP;
   if (total <= 0) return cudaSuccess;
-  mlp_gather_planes_kernel<<<(total + 7) / 8, 256, 0, stream>>>(p, reinterpret_cast<__nv_bfloat16*>(a_hi),
-                                                               reinterpret_cast<__nv_bfloat16*>(a_lo), total);
+  mlp_gather_planes_kernel<<<(total + 7) / 8, 256, 0, stream>>>(p, reinterpret_cast<__half*>(a_hi),
+                                                               reinterpret_cast<__half*>(a_lo), total);
   return cudaGetLastError();
 }
 

@@ -18,6 +18,7 @@
 #include "gigapose_kernels.h"
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace gp {
 
@@ -97,7 +98,7 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int passes = p.passes;
   const int bn = p.bn > 0 ? p.bn : kBN;                     // 128 / 192 / 256 output columns per tile
-  const uint32_t idesc = umma_idesc_f16(kTileM, bn, 1);
+  const uint32_t idesc = umma_idesc_f16(kTileM, bn, p.f16 ? 0 : 1);   // A / B formats: bf16 (1) or fp16 (0) hi / lo planes
   const int num_m = (p.M + kTileM - 1) / kTileM, num_n = p.N / bn;
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;     // 0 = leader of the pair
   const int first_tile = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -354,9 +355,16 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             float a = v[j], b = v[j + 1];
             if (p.mode == GEMM_PLANES_GELU) { a = gelu_erf(a); b = gelu_erf(b); }
             if (p.mode == GEMM_PLANES_RELU || p.mode == GEMM_PLANES_ADD_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-            const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-            hi[j >> 1] = pack_bf16(ah, bh);
-            lo[j >> 1] = pack_bf16(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
+            if (p.f16) {
+              const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
+              hi[j >> 1] = (uint32_t)__half_as_ushort(ah) | ((uint32_t)__half_as_ushort(bh) << 16);
+              lo[j >> 1] = (uint32_t)__half_as_ushort(__float2half_rn(a - __half2float(ah))) |
+                           ((uint32_t)__half_as_ushort(__float2half_rn(b - __half2float(bh))) << 16);
+            } else {
+              const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+              hi[j >> 1] = pack_bf16(ah, bh);
+              lo[j >> 1] = pack_bf16(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
+            }
           }
           size_t dst = out_row * p.N + n;
           if (p.mode == GEMM_QKV_HEADS) {   // head-major: [q|k|v][crop][head][token][64] so that attention tiles are contiguous

@@ -4,6 +4,7 @@
 #include "gigapose_kernels.h"
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace gp {
 
@@ -26,6 +27,19 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long long rows,
   const long long r = i / Kpad;
   const int k = (int)(i - r * Kpad);
   split_store(k < K ? x[r * K + k] : 0.f, hi, lo, (size_t)i);
+}
+
+// same with IEEE fp16 hi / lo (x = hi + lo to ~2^-22 for |x| in [6e-5, 6e4]; smaller values keep 6e-8 absolute)
+__global__ void split_planes_f16_kernel(const float* __restrict__ x, long long rows, int K, int Kpad, __half* __restrict__ hi,
+                                        __half* __restrict__ lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * Kpad) return;
+  const long long r = i / Kpad;
+  const int k = (int)(i - r * Kpad);
+  const float v = k < K ? x[r * K + k] : 0.f;
+  const __half h = __float2half_rn(v);
+  hi[i] = h;
+  lo[i] = __float2half_rn(v - __half2float(h));
 }
 
 // ---------------------------------------------------------------- im2col: [b,3,224,224] -> planes [b*256, 608]
@@ -107,9 +121,15 @@ layernorm_planes_kernel(const float* __restrict__ x, int M, const float* __restr
 
 }  // namespace
 
-cudaError_t launch_split_planes(const float* x, long long rows, int K, int Kpad, uint16_t* hi, uint16_t* lo, cudaStream_t s) {
+cudaError_t launch_split_planes(const float* x, long long rows, int K, int Kpad, uint16_t* hi, uint16_t* lo, cudaStream_t s,
+                                bool f16) {
   const long long total = rows * Kpad;
   if (total <= 0) return cudaSuccess;
+  if (f16) {
+    split_planes_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, rows, K, Kpad, reinterpret_cast<__half*>(hi),
+                                                                           reinterpret_cast<__half*>(lo));
+    return cudaGetLastError();
+  }
   split_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, rows, K, Kpad, reinterpret_cast<__nv_bfloat16*>(hi),
                                                                      reinterpret_cast<__nv_bfloat16*>(lo));
   return cudaGetLastError();

@@ -165,6 +165,8 @@ class ShardedRetriever:
         eng.set_poses(torch.stack(Ks).float(), torch.stack(Ms).float(), torch.stack(Ps).float())
         eng.set_ist_weights(model.ist_net.regressor)
         self._bufs = {}
+        self._graphs = {}
+        self.use_cuda_graph = False
         self._copy_stream = None
         self._ring = {"slot": 0, "bufs": {}}
 
@@ -181,7 +183,7 @@ class ShardedRetriever:
         return b
 
     @torch.no_grad()
-    def retrieve(self, tar_img_window, tar_mask, q_obj, tar_K_window, tar_M_window):
+    def retrieve(self, tar_img_window, tar_mask, q_obj, tar_K_window, tar_M_window, mark=lambda name: None):
         """`tar_img_window`, `tar_K_window`, `tar_M_window`: this rank's detections `window(B, rank, world)`;
         `tar_mask` [B,H,W] and `q_obj` [B] hold the full batch (every rank searches all B queries).  Returns the
         predictions of the window (dict of [n,k,...] tensors, n = hi - lo)."""
@@ -194,25 +196,60 @@ class ShardedRetriever:
         per, tok = buf["per"], buf["tok"]
         # a1 + a6 on the rank's own crops; only the ViT descriptors travel
         ist = None
+        mark("start")
         if n > 0:
             tok[r * per: r * per + n].copy_(self.model.ae_net.patch_tokens(tar_img_window))
+            mark("a1_vit")
             ist = self.model.ist_net.forward_by_chunk(tar_img_window)
+            mark("a6_ist_backbone")
         if G > 1:
             eng.allgather(tok[r * per: (r + 1) * per], tok)
+            mark("allgather_query_descriptors")
         # a4 on the local descriptor shard -> light candidate records in this rank's slot, then THE collective + merge
         eng.set_queries(tok[:B], tar_mask, q_obj, norm_passes=1)
         eng.sim_candidates(out=buf["mine"])
+        mark("a4_similarity_local_topk")
         if G > 1:
             m = eng.topk_allgather_merge(buf["packed"], buf["total"], buf["slot0"])
         else:
             m = eng.topk_merge(dict(buf["slot0"], rel_scale=None, rel_inplane=None), G=1)
+        mark("allgather_topk_records_merge")
         if n == 0:
             return None
         # a5, a7-a9 for the rank's own detections only (the IST bank is replicated, so every winner is local)
         mw = {k: v[lo:hi] for k, v in m.items()}
         rs, ri = eng.ist_mlp(ist, mw, b0=lo)
+        mark("a5_ist_mlp")
         rr = eng.ransac(mw, rs, ri)
-        return eng.sort_and_pose(tar_K_window, tar_M_window, mw, rs, ri, rr, b0=lo)
+        out = eng.sort_and_pose(tar_K_window, tar_M_window, mw, rs, ri, rr, b0=lo)
+        mark("a7_a8_a9_ransac_sort_pose")
+        return out
+
+    def retrieve_graphed(self, tar_img_window, tar_mask, q_obj, tar_K_window, tar_M_window):
+        """`retrieve` replayed as ONE CUDA graph per batch shape: the ~200 kernel launches AND the two in-library NCCL
+        all-gathers of a step are captured together (NCCL collectives are capturable; every rank replays the same
+        graph).  Outputs are copies of the graph's static tensors."""
+        key = (tar_img_window.shape[0], tar_mask.shape[0])
+        entry = self._graphs.get(key)
+        cur = torch.cuda.current_stream(self.device)
+        args = (tar_img_window, tar_mask, q_obj, tar_K_window, tar_M_window)
+        if entry is None:
+            static = [t.clone() for t in args]
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):                                   # warm-up outside the capture (NCCL connections, buffers)
+                    self.retrieve(*static)
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.retrieve(*static)
+            entry = self._graphs[key] = (graph, static, out)
+        graph, static, out = entry
+        for dst, src in zip(static, args):
+            dst.copy_(src, non_blocking=True)
+        graph.replay()
+        return None if out is None else {k: v.clone() for k, v in out.items()}
 
     # ---- host <-> device pipelining (same contract as GigaPose.stage / fetch_async)
     def stage(self, batch):
@@ -242,7 +279,8 @@ class ShardedRetriever:
         for t in staged.values():
             if torch.is_tensor(t):
                 t.record_stream(cur)
-        return self.retrieve(staged["img"], staged["mask"], staged["q_obj"], staged["K"], staged["M"])
+        fn = self.retrieve_graphed if self.use_cuda_graph else self.retrieve
+        return fn(staged["img"], staged["mask"], staged["q_obj"], staged["K"], staged["M"])
 
     def fetch_async(self, out):
         """Device -> pinned host copy of this rank's poses + scores; `.result()` waits for it."""
@@ -299,14 +337,16 @@ def run_sharded_bench(args, cfg, config, wl_name, rank, world, device, METRIC, U
     q_obj = (labels - 1).to(device)
     K, M = dev(batch_host.tar_K[lo:hi]), dev(batch_host.tar_M[lo:hi])
 
-    def step_resident():
-        return retr.retrieve(img, mask, q_obj, K, M)
+    retr.use_cuda_graph = bool(getattr(args, "multi_gpu_graph", False))
 
+    def step_resident():
+        return (retr.retrieve_graphed if retr.use_cuda_graph else retr.retrieve)(img, mask, q_obj, K, M)
+
+    l0 = retr.eng.launch_count()
+    retr.retrieve(img, mask, q_obj, K, M)                 # launches of this library per step, counted on one eager step
+    launches = retr.eng.launch_count() - l0
     for _ in range(args.warmup):
         step_resident()
-    l0 = retr.eng.launch_count()
-    step_resident()
-    launches = retr.eng.launch_count() - l0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(device.index) as clocks:
         torch.cuda.synchronize()
@@ -350,6 +390,18 @@ def run_sharded_bench(args, cfg, config, wl_name, rank, world, device, METRIC, U
     e2e_t = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], device=device)
     dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_t)
+    # per-stage CUDA-event times of one extra eager step on every rank (diagnostic: names the scaling limiter)
+    marks = []
+
+    def mark(name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        marks.append((name, e))
+
+    dist.barrier()
+    retr.retrieve(img, mask, q_obj, K, M, mark=mark)
+    torch.cuda.synchronize()
+    stage_ms = {n1: round(e0_.elapsed_time(e1_), 3) for (n0, e0_), (n1, e1_) in zip(marks[:-1], marks[1:])}
     sim_ms = retr.eng.time_sim_kernel(iters=10)
     sim_t = torch.tensor([sim_ms], device=device)
     dist.all_reduce(sim_t, op=dist.ReduceOp.MAX)
@@ -382,12 +434,12 @@ def run_sharded_bench(args, cfg, config, wl_name, rank, world, device, METRIC, U
                                                    "query descriptors + 1 all-gather of top-k records (in the library, "
                                                    "NCCL over NVLink)",
                                **{kk: (vv + ["e"] if kk == "native_rows" else vv) for kk, vv in bench.rows_config().items()},
-                               planted_view_in_topk=hit, cuda_graph=False),
+                               planted_view_in_topk=hit, cuda_graph=bool(retr.use_cuda_graph)),
                 "clocks": clocks.summary(),
                 "e2e": {"value": B / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms,
                         "note": "bytes summed over ranks; every rank uploads its own crop window + the batch's masks"},
-                "gpu_launches": int(launches),
+                "gpu_launches": int(launches), "stage_ms_rank0": stage_ms,
                 "roofline": ({"bound": "hbm", "kernel": "sim_search_kernel", "achieved": alg_bytes / (float(sim_t) / 1e3) / 1e9,
                               "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
                               "frac": alg_bytes / (float(sim_t) / 1e3) / 1e9 / peaks.get("hbm_gbs", 6650.0), "traffic": None,

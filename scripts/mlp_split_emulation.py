@@ -21,14 +21,14 @@ from helpers import engine_from_case  # noqa: E402
 from oracle import port  # noqa: E402  (weights container only)
 
 
-def split(x):
-    hi = x.to(torch.bfloat16).float()
-    return hi, (x - hi).to(torch.bfloat16).float()
+def split(x, dt=torch.bfloat16):
+    hi = x.to(dt).float()
+    return hi, (x - hi).to(dt).float()
 
 
-def linear_split(a, w, b, passes):
-    ah, al = split(a)
-    wh, wl = split(w)
+def linear_split(a, w, b, passes, dt=torch.bfloat16):
+    ah, al = split(a, dt)
+    wh, wl = split(w, dt)
     y = ah @ wh.t()
     if passes == 3:
         y = y + ah @ wl.t() + al @ wh.t()
@@ -62,11 +62,11 @@ def main():
         ft = bank_ist[obj, tid, :, sp[:, 1], sp[:, 0]]
         x = torch.cat([fq, ft], dim=1)                                               # [rows,512]
         out = {"hypotheses": int(B * 5), "valid_rows": int(x.shape[0])}
-        for mode, passes in (("split_bf16_x3", 3), ("plain_bf16", 1)):
+        for mode, passes, dt in (("split_bf16_x3", 3, torch.bfloat16), ("split_f16_x3", 3, torch.float16), ("plain_bf16", 1, torch.bfloat16)):
             heads = []
             for head in (reg.scale_predictor, reg.inplane_predictor):
-                h = torch.relu(linear_split(x, head[0].weight, head[0].bias, passes))
-                h = torch.relu(linear_split(h, head[2].weight, head[2].bias, passes))
+                h = torch.relu(linear_split(x, head[0].weight, head[0].bias, passes, dt))
+                h = torch.relu(linear_split(h, head[2].weight, head[2].bias, passes, dt))
                 heads.append(h @ head[4].weight.t() + head[4].bias)                  # fp32 head, as the kernel would keep it
             rs2 = torch.full_like(rs, -1000.0)
             ri2 = torch.full_like(ri, -1000.0)

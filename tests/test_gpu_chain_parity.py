@@ -143,8 +143,8 @@ def test_crop_level_chain_matches_oracle():
     assert int(same_k.sum()) >= int(0.85 * B * 5) and int(cnt_diff.max()) <= 2, report["fp32_split"]
     assert torch.equal(out["idx_failed"][same_k], failed_o[same_k])
     # (the regressor has random weights: |M| reaches 1e4, so the bound is relative to each matrix' largest entry)
-    dM = (out["M"] - M_o).abs().flatten(2).max(-1)
-    assert bool((dM <= 2e-5 * M_o.abs().flatten(2).max(-1) + 2e-3)[same_k].all()), float(dM[same_k].max())
+    dM = (out["M"] - M_o).abs().flatten(2).amax(-1)
+    assert bool((dM <= 2e-5 * M_o.abs().flatten(2).amax(-1) + 2e-3)[same_k].all()), float(dM[same_k].max())
     poses_o = port.pose_recovery(labels, batch.tar_K, batch.tar_M, out["id_src"], out["M"].clone(), ref_in["template_K"],
                                  ref_in["template_Ms"], ref_in["template_poses"])
     err = (out["pred_poses"] - poses_o).abs()
@@ -158,7 +158,7 @@ def test_crop_level_chain_matches_oracle():
                               for kk in range(5)] for b in range(B)])
     perr = (_by_template(out, ref, "pred_poses") - ref["pred_poses"]).abs()
     perr[..., :3, 3] /= ref["pred_poses"][..., :3, 3].abs().clamp(min=1.0)
-    perr = perr.flatten(2).max(dim=2).values
+    perr = perr.flatten(2).amax(-1)
     d_count = (_by_template(out, ref, "ransac_scores").sum(-1) - ref["ransac_scores"].sum(-1)).abs()
     report["fp32_split"].update(hypotheses_with_identical_inlier_set=int(same_set.sum()),
                                 max_inlier_count_difference=int(d_count.max()),
