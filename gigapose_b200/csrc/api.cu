@@ -462,6 +462,10 @@ int gp_bank_set_poses(gp_handle_t h, const float* K, const float* M, const float
   return GP_OK;
 }
 
+// The regressor's weights (|w| ~ 0.03) are stored as fp16 pairs of 64 w: the lo half of an unscaled weight would be an fp16
+// subnormal (6e-8 absolute precision, i.e. only ~2^-19 of the weight); the GEMM epilogue multiplies by 1/64 (exact).
+static constexpr float kMlpWeightScale = 64.0f;
+
 int gp_set_ist_weights(gp_handle_t h, const float* const w[12], int use_tanh, void* stream) {
   if (!h || !w) return fail(GP_ERR_INVALID, "null argument");
   for (int i = 0; i < 12; ++i)
@@ -473,10 +477,10 @@ int gp_set_ist_weights(gp_handle_t h, const float* const w[12], int use_tanh, vo
   // tensor-core form: both heads' first layers side by side as one [1024,512] operand, bf16 hi / lo planes
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Workspace& ws = h->ws;
-  GP_CUDA(gp::launch_split_planes(w[0], 512, 512, 512, ws.w1_hi, ws.w1_lo, s, true));   // fp16 hi / lo (see gp_ist_mlp)
-  GP_CUDA(gp::launch_split_planes(w[6], 512, 512, 512, ws.w1_hi + 512 * 512, ws.w1_lo + 512 * 512, s, true));
-  GP_CUDA(gp::launch_split_planes(w[2], 256, 512, 512, ws.w2s_hi, ws.w2s_lo, s, true));
-  GP_CUDA(gp::launch_split_planes(w[8], 256, 512, 512, ws.w2i_hi, ws.w2i_lo, s, true));
+  GP_CUDA(gp::launch_split_planes(w[0], 512, 512, 512, ws.w1_hi, ws.w1_lo, s, true, kMlpWeightScale));   // fp16 hi / lo (see gp_ist_mlp)
+  GP_CUDA(gp::launch_split_planes(w[6], 512, 512, 512, ws.w1_hi + 512 * 512, ws.w1_lo + 512 * 512, s, true, kMlpWeightScale));
+  GP_CUDA(gp::launch_split_planes(w[2], 256, 512, 512, ws.w2s_hi, ws.w2s_lo, s, true, kMlpWeightScale));
+  GP_CUDA(gp::launch_split_planes(w[8], 256, 512, 512, ws.w2i_hi, ws.w2i_lo, s, true, kMlpWeightScale));
   GP_CUDA(cudaMemcpyAsync(ws.bias1, w[1], 512 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   GP_CUDA(cudaMemcpyAsync(ws.bias1 + 512, w[7], 512 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   g_launches += 4;
@@ -611,11 +615,11 @@ int gp_ist_mlp(gp_handle_t h, int b0, int n, const float* q_ist, int ist_layout,
   float* h2i = h->ws.hidden2 + max_rows * 256;
   GP_CUDA(gp::launch_mlp_gather_planes(p, h->ws.mlp_a_hi, h->ws.mlp_a_lo, s));
   gp::GemmParams g{};
-  g.passes = 3; g.pair = 1; g.f16 = 1;
+  g.passes = 3; g.pair = 1; g.f16 = 1; g.acc_scale = 1.0f / kMlpWeightScale;
   g.M = rows; g.N = 1024; g.K = 512; g.mode = gp::GEMM_PLANES_RELU; g.bias = h->ws.bias1; g.out_hi = h1_hi; g.out_lo = h1_lo;
   GP_CUDA(gp::launch_vit_gemm(h->tm_ma_hi, h->tm_ma_lo, h->tm_w1_hi, h->tm_w1_lo, g, h->num_sms, s));
   g = gp::GemmParams{};
-  g.passes = 3; g.pair = 1; g.f16 = 1;
+  g.passes = 3; g.pair = 1; g.f16 = 1; g.acc_scale = 1.0f / kMlpWeightScale;
   g.M = rows; g.N = 256; g.K = 512; g.mode = gp::GEMM_ROWS_F32_RELU; g.bias = h->mlp.s_b2; g.x = h2s;
   GP_CUDA(gp::launch_vit_gemm(h->tm_h1s_hi, h->tm_h1s_lo, h->tm_w2s_hi, h->tm_w2s_lo, g, h->num_sms, s));
   g.bias = h->mlp.i_b2; g.x = h2i;

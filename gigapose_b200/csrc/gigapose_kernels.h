@@ -207,13 +207,14 @@ struct GemmParams {
   int swap;                   // rows of C = output channels (M = cout, a [cout, K] filter bank as the 128-row operand),
                               // columns = output pixels (N); outputs are still written as NHWC planes [N, M]
   const uint16_t *res_hi, *res_lo;   // GEMM_PLANES_ADD_RELU: shortcut planes [M,N]
+  float acc_scale;            // 0 = off; else C = acc * acc_scale + bias (exact power of two undoing a scaled W operand)
   int f16;                    // operand (and output) planes hold IEEE fp16 hi/lo pairs instead of bf16: 22 significant bits
                               // for O(1)-range data (the IST MLP), kind::f16 instruction with fp16 A/B formats
 };
 cudaError_t launch_vit_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                             const CUtensorMap& w_lo, const GemmParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_split_planes(const float* x, long long rows, int K, int Kpad, uint16_t* hi, uint16_t* lo, cudaStream_t s,
-                                bool f16 = false);
+                                bool f16 = false, float pre_scale = 1.0f);
 cudaError_t launch_im2col(const float* img, int b, int Kpad, uint16_t* hi, uint16_t* lo, cudaStream_t s);
 cudaError_t launch_cls_rows(const float* cls, const float* pos, int b, float* x, cudaStream_t s);
 cudaError_t launch_layernorm_planes(const float* x, int M, const float* w, const float* b, float eps, uint16_t* hi,

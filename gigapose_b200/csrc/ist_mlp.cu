@@ -192,7 +192,11 @@ mlp_gather_planes_kernel(IstMlpParams p, __half* __restrict__ a_hi, __half* __re
       // IEEE fp16 hi / lo: 22 significant bits for these O(1) descriptors (bf16 pairs carry 16), same tensor rate
       __half h[4], l[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { h[j] = __float2half_rn(x[j]); l[j] = __float2half_rn(x[j] - __half2float(h[j])); }
+      for (int j = 0; j < 4; ++j) {
+        const float xs = fminf(fmaxf(x[j], -65504.f), 65504.f);            // saturate instead of inf
+        h[j] = __float2half_rn(xs);
+        l[j] = __float2half_rn(xs - __half2float(h[j]));
+      }
       const size_t o = (size_t)row * 512 + part * 256 + c;
       *reinterpret_cast<uint2*>(a_hi + o) = make_uint2((uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
                                                        (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));

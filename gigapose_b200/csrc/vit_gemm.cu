@@ -336,7 +336,8 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         const int n = n0 + c0;
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(v32[j]) + sb[c0 + j];
+        for (int j = 0; j < 32; ++j)
+          v[j] = (p.acc_scale != 0.f ? __uint_as_float(v32[j]) * p.acc_scale : __uint_as_float(v32[j])) + sb[c0 + j];
         if (p.mode == GEMM_PLANES || p.mode == GEMM_PLANES_GELU || p.mode == GEMM_QKV_HEADS || p.mode == GEMM_PLANES_RELU ||
             p.mode == GEMM_PLANES_ADD_RELU) {
           uint32_t hi[16], lo[16];
@@ -355,7 +356,9 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             float a = v[j], b = v[j + 1];
             if (p.mode == GEMM_PLANES_GELU) { a = gelu_erf(a); b = gelu_erf(b); }
             if (p.mode == GEMM_PLANES_RELU || p.mode == GEMM_PLANES_ADD_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-            if (p.f16) {
+            if (p.f16) {                             // saturating: a value beyond the fp16 range stays finite (and wrong) instead of inf
+              a = fminf(fmaxf(a, -65504.f), 65504.f);
+              b = fminf(fmaxf(b, -65504.f), 65504.f);
               const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
               hi[j >> 1] = (uint32_t)__half_as_ushort(ah) | ((uint32_t)__half_as_ushort(bh) << 16);
               lo[j >> 1] = (uint32_t)__half_as_ushort(__float2half_rn(a - __half2float(ah))) |

@@ -30,13 +30,14 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long long rows,
 }
 
 // same with IEEE fp16 hi / lo (x = hi + lo to ~2^-22 for |x| in [6e-5, 6e4]; smaller values keep 6e-8 absolute)
-__global__ void split_planes_f16_kernel(const float* __restrict__ x, long long rows, int K, int Kpad, __half* __restrict__ hi,
-                                        __half* __restrict__ lo) {
+__global__ void split_planes_f16_kernel(const float* __restrict__ x, long long rows, int K, int Kpad, float pre_scale,
+                                        __half* __restrict__ hi, __half* __restrict__ lo) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * Kpad) return;
   const long long r = i / Kpad;
   const int k = (int)(i - r * Kpad);
-  const float v = k < K ? x[r * K + k] : 0.f;
+  // pre_scale (a power of two, exact) lifts small weights into the range where the lo half is a NORMAL fp16 number
+  const float v = fminf(fmaxf((k < K ? x[r * K + k] : 0.f) * pre_scale, -65504.f), 65504.f);
   const __half h = __float2half_rn(v);
   hi[i] = h;
   lo[i] = __float2half_rn(v - __half2float(h));
@@ -122,11 +123,11 @@ layernorm_planes_kernel(const float* __restrict__ x, int M, const float* __restr
 }  // namespace
 
 cudaError_t launch_split_planes(const float* x, long long rows, int K, int Kpad, uint16_t* hi, uint16_t* lo, cudaStream_t s,
-                                bool f16) {
+                                bool f16, float pre_scale) {
   const long long total = rows * Kpad;
   if (total <= 0) return cudaSuccess;
   if (f16) {
-    split_planes_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, rows, K, Kpad, reinterpret_cast<__half*>(hi),
+    split_planes_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, rows, K, Kpad, pre_scale, reinterpret_cast<__half*>(hi),
                                                                            reinterpret_cast<__half*>(lo));
     return cudaGetLastError();
   }
