@@ -45,7 +45,9 @@ def _compare(out, ref, pose_tol=1e-3):
         if not torch.equal(a, b.to(a.dtype)):
             bad[k] = int((a != b.to(a.dtype)).sum())
     for k in FLOAT_KEYS:
-        tol = pose_tol if k == "pred_poses" else 2e-5
+        # M: the regressor's hidden layers run on tensor cores (fp16 hi/lo pairs, ~2e-5 on sigma: accumulation in the
+        # tensor core truncates), everything else is fp32 SIMT
+        tol = pose_tol if k == "pred_poses" else (5e-5 if k in ("M", "relScale", "relInplane") else 2e-5)
         scale = 1.0
         if k == "pred_poses":                       # translations are in mm (~400): relative 1e-3 on t, abs on R
             d = (out[k] - ref[k]).abs()
@@ -187,7 +189,15 @@ def test_tensor_core_mlp_keeps_every_integer_output(monkeypatch):
     valid = a["src_pts"][..., 0] != -1
     assert torch.equal(a["relScale"] == -1000, b["relScale"] == -1000)
     d = max(float((a["relScale"] - b["relScale"])[valid].abs().max()), float((a["relInplane"] - b["relInplane"])[valid].abs().max()))
-    assert d < 1e-4, d
+    perr = (a["pred_poses"] - b["pred_poses"]).abs()
+    perr[..., :3, 3] /= a["pred_poses"][..., :3, 3].abs().clamp(min=1.0)
+    from helpers import write_report
+    write_report("mlp_tc_vs_simt.json", {"case": "c2 planted features (32 detections, 8 x 162 templates)", "hypotheses": 160,
+                                         "valid_correspondences": int(valid.sum()), "regressor_output_max_abs_diff": d,
+                                         "pose_max_diff": float(perr.max()),
+                                         "integer_outputs_changed": int(sum((a[k] != b[k]).sum() for k in INT_KEYS))})
+    assert d < 2e-5, d
+    assert float(perr.max()) < 2e-4
     for k in INT_KEYS:
         assert torch.equal(a[k], b[k]), k
     assert torch.equal(a["scores"], b["scores"])
