@@ -362,8 +362,6 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch the per-batch kernel sequence eagerly")
-    ap.add_argument("--multi-gpu-graph", action="store_true",
-                    help="N > 1: replay each rank's step (kernels + the two in-library NCCL all-gathers) as one CUDA graph")
     ap.add_argument("--profile-range", action="store_true",
                     help="wrap ONE extra resident step in cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()

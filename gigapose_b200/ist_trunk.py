@@ -60,9 +60,8 @@ def folded_convs_in_abi_order(resnet, device):
 
 
 def _version_key(resnet):
-    probes = (resnet.conv1.weight, resnet.bn1.running_var, resnet.layer1[0].conv1.weight, resnet.layer4[1].bn2.running_mean,
-              resnet.layer4_outconv.weight)
-    return tuple((p.data_ptr(), int(p._version)) for p in probes)
+    """Staleness key over every parameter and BatchNorm buffer (storage address + in-place version counter)."""
+    return hash(tuple((t.data_ptr(), int(t._version)) for t in list(resnet.parameters()) + list(resnet.buffers())))
 
 
 class NativeISTTrunk:

@@ -290,13 +290,21 @@ class GigaPose(LightningModule):
         mark("a7_a8_a9_ransac_sort_pose")
         return out
 
+    GRAPH_BUCKET = 4          # batch sizes are padded to a multiple of this before graph capture / replay
+
     def _graphed_chunk(self, eng, dataset_name, tar_img, tar_mask, q_obj, tar_K, tar_M, sort=True):
-        """Static input buffers + one captured graph per (dataset, batch size); outputs are copies of the graph's
-        static tensors."""
-        key = (dataset_name, tar_img.shape[0], bool(sort))
+        """Static input buffers + one captured graph per (dataset, padded batch size); outputs are copies of the graph's
+        static tensors.  The reference's test loop hands over a different number of detections per image
+        (test.py:55-60): batch sizes are padded to the next multiple of GRAPH_BUCKET by repeating the last detection
+        (detections are independent, so the first B rows are unaffected) and the outputs sliced, which bounds the
+        number of captures at max_dets_per_call / GRAPH_BUCKET."""
+        B = tar_img.shape[0]
+        Bp = min(-(-B // self.GRAPH_BUCKET) * self.GRAPH_BUCKET, eng.max_batch)
+        key = (dataset_name, Bp, bool(sort))
         entry = self._graphs.get(key)
+        args = (tar_img, tar_mask, q_obj, tar_K, tar_M)
         if entry is None:
-            static = [t.clone() for t in (tar_img, tar_mask, q_obj, tar_K, tar_M)]
+            static = [torch.cat([t, t[-1:].expand(Bp - B, *t.shape[1:])]).contiguous() if Bp > B else t.clone() for t in args]
             side = torch.cuda.Stream(device=eng.device)
             side.wait_stream(torch.cuda.current_stream(eng.device))
             with torch.cuda.stream(side):
@@ -309,12 +317,14 @@ class GigaPose(LightningModule):
             entry = (graph, static, out)
             self._graphs[key] = entry
         graph, static, out = entry
-        for dst, src in zip(static, (tar_img, tar_mask, q_obj, tar_K, tar_M)):
-            dst.copy_(src, non_blocking=True)
+        for dst, src in zip(static, args):
+            dst[:B].copy_(src, non_blocking=True)
+            if Bp > B:
+                dst[B:].copy_(src[-1:].expand(Bp - B, *src.shape[1:]), non_blocking=True)
         graph.replay()
         # the graph's static output tensors are overwritten by the next replay of the same batch size (the next chunk
         # of this call, or the next call): hand out copies (110 KB per detection)
-        return {k: v.clone() for k, v in out.items()}
+        return {k: v[:B].clone() for k, v in out.items()}
 
     def stage(self, batch, dataset_name):
         """Start the host->device copy of a (pinned) batch on a dedicated copy stream and return the device-resident

@@ -243,3 +243,23 @@ def test_cuda_graph_with_more_than_one_chunk():
     other, _, _ = bench.make_queries(templates, 8, seed=7)
     model.retrieve(other, "synthetic")
     assert torch.equal(graphed.pred_poses, keep)
+
+
+def test_cuda_graph_batch_size_buckets():
+    """Batch sizes 5, 6, 7 share ONE captured graph (padded to 8) and give the eager results."""
+    sys.path.insert(0, ROOT)
+    import bench
+    model = bench.build_models(torch.device(DEV))
+    templates = bench.SyntheticTemplates(2, 8, torch.device(DEV))
+    model.template_datasets = {"synthetic": templates}
+    model.test_dataset_name = "synthetic"
+    for B in (5, 6, 7):
+        batch, labels, views = bench.make_queries(templates, B, seed=20 + B)
+        model.use_cuda_graph = False
+        eager = model.retrieve(batch, "synthetic")
+        model.use_cuda_graph = True
+        graphed = model.retrieve(batch, "synthetic")
+        for k in ("id_src", "src_pts", "scores", "pred_poses", "ransac_scores"):
+            assert getattr(graphed, k).shape[0] == B
+            assert torch.equal(getattr(graphed, k).cpu(), getattr(eager, k).cpu()), (B, k)
+    assert len(model._graphs) == 1
