@@ -603,7 +603,7 @@ int gp_ist_mlp(gp_handle_t h, int b0, int n, const float* q_ist, int ist_layout,
     g_launches += 4;
     return GP_OK;
   }
-  // tensor-core form: dense rows (row = flat (b,k,t), zeros where invalid) -> 512 -> [512 | 512] -> 256 + 256 -> heads.
+  // tensor-core form: compacted valid rows (device-side count, no host sync) -> 512 -> [512 | 512] -> 256 + 256 -> heads.
   // Operands are IEEE fp16 hi / lo pairs (not bf16): descriptors, weights and hidden activations of this regressor are
   // O(1e-2 .. 1e2), where an fp16 pair carries 22 significant bits -- the regressor outputs then agree with fp32 to ~5e-6
   // (bf16 pairs: 4e-5, which moved a pose component by 1.2e-3 on the parity suite), at the same tensor rate.
@@ -615,17 +615,17 @@ int gp_ist_mlp(gp_handle_t h, int b0, int n, const float* q_ist, int ist_layout,
   float* h2i = h->ws.hidden2 + max_rows * 256;
   GP_CUDA(gp::launch_mlp_gather_planes(p, h->ws.mlp_a_hi, h->ws.mlp_a_lo, s));
   gp::GemmParams g{};
-  g.passes = 3; g.pair = 1; g.f16 = 1; g.acc_scale = 1.0f / kMlpWeightScale;
+  g.passes = 3; g.pair = 1; g.f16 = 1; g.acc_scale = 1.0f / kMlpWeightScale; g.m_dev = h->ws.row_count;
   g.M = rows; g.N = 1024; g.K = 512; g.mode = gp::GEMM_PLANES_RELU; g.bias = h->ws.bias1; g.out_hi = h1_hi; g.out_lo = h1_lo;
   GP_CUDA(gp::launch_vit_gemm(h->tm_ma_hi, h->tm_ma_lo, h->tm_w1_hi, h->tm_w1_lo, g, h->num_sms, s));
   g = gp::GemmParams{};
-  g.passes = 3; g.pair = 1; g.f16 = 1; g.acc_scale = 1.0f / kMlpWeightScale;
+  g.passes = 3; g.pair = 1; g.f16 = 1; g.acc_scale = 1.0f / kMlpWeightScale; g.m_dev = h->ws.row_count;
   g.M = rows; g.N = 256; g.K = 512; g.mode = gp::GEMM_ROWS_F32_RELU; g.bias = h->mlp.s_b2; g.x = h2s;
   GP_CUDA(gp::launch_vit_gemm(h->tm_h1s_hi, h->tm_h1s_lo, h->tm_w2s_hi, h->tm_w2s_lo, g, h->num_sms, s));
   g.bias = h->mlp.i_b2; g.x = h2i;
   GP_CUDA(gp::launch_vit_gemm(h->tm_h1i_hi, h->tm_h1i_lo, h->tm_w2i_hi, h->tm_w2i_lo, g, h->num_sms, s));
   GP_CUDA(gp::launch_mlp_head_rows(h->mlp, p, h2s, h2i, s));
-  g_launches += 5;
+  g_launches += 6;
   return GP_OK;
 }
 

@@ -130,9 +130,11 @@ struct IstMlpParams {
 };
 cudaError_t launch_ist_mlp(const IstMlpWeights& w, const IstMlpParams& p, cudaStream_t stream);
 // Tensor-core form of the two hidden layers (vit_gemm_kernel on bf16 hi/lo planes, fp32-faithful 3-pass products):
-//  * gather: row (b,k,t) = cat(query IST descriptor at tar_pt, template IST descriptor at src_pt) -> planes [B*k*256, 512]
-//    (zeros for invalid correspondences: no compaction, the row index IS the flat (b,k,t) index);
-//  * head: scale = h2_s . w3 + b ; (cos, sin) = tanh(h2_i . W3 + b) in fp32, -1000 where invalid (ist_net.py:110-113).
+//  * compact (device-side, no host round trip) + gather: row r = cat(query IST descriptor at tar_pt, template IST descriptor
+//    at src_pt) of the r-th valid correspondence -> planes [rows, 512]; *p.row_count rows, the GEMMs read that count
+//    on the device (GemmParams::m_dev);
+//  * head: scale = h2_s . w3 + b ; (cos, sin) = tanh(h2_i . W3 + b) in fp32, scattered to (b,k,t); -1000 where invalid
+//    (ist_net.py:110-113) is written by the compaction pass.
 cudaError_t launch_mlp_gather_planes(const IstMlpParams& p, uint16_t* a_hi, uint16_t* a_lo, cudaStream_t stream);
 cudaError_t launch_mlp_head_rows(const IstMlpWeights& w, const IstMlpParams& p, const float* h2_scale, const float* h2_inplane,
                                  cudaStream_t stream);
@@ -207,6 +209,7 @@ struct GemmParams {
   int swap;                   // rows of C = output channels (M = cout, a [cout, K] filter bank as the 128-row operand),
                               // columns = output pixels (N); outputs are still written as NHWC planes [N, M]
   const uint16_t *res_hi, *res_lo;   // GEMM_PLANES_ADD_RELU: shortcut planes [M,N]
+  const int* m_dev;           // nullable: the row count M lives on the device (data-dependent GEMM size; p.M = upper bound)
   float acc_scale;            // 0 = off; else C = acc * acc_scale + bias (exact power of two undoing a scaled W operand)
   int f16;                    // operand (and output) planes hold IEEE fp16 hi/lo pairs instead of bf16: 22 significant bits
                               // for O(1)-range data (the IST MLP), kind::f16 instruction with fp16 A/B formats

@@ -164,30 +164,26 @@ mlp_head_kernel(IstMlpParams p, IstMlpWeights w, int max_rows) {
   }
 }
 
-// ---- tensor-core form: gather into bf16 hi/lo planes (one warp per correspondence slot) --------------------------------
+// ---- tensor-core form: gather the compacted rows into fp16 hi/lo planes (one warp per valid correspondence) ---------------
 __global__ void __launch_bounds__(256)
-mlp_gather_planes_kernel(IstMlpParams p, __half* __restrict__ a_hi, __half* __restrict__ a_lo, int total) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+mlp_gather_planes_kernel(IstMlpParams p, __half* __restrict__ a_hi, __half* __restrict__ a_lo, int max_rows) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= total) return;
-  const long long sx = p.src_pts[2 * (size_t)row], sy = p.src_pts[2 * (size_t)row + 1];
-  const bool valid = (sx != -1) && (sy != -1);
-  const float* q = nullptr;
-  const float* t = nullptr;
-  if (valid) {
-    const int bk = row >> 8, b = bk / p.k;
-    const long long tx = p.tar_pts[2 * (size_t)row], ty = p.tar_pts[2 * (size_t)row + 1];
-    const long long lid = (p.id_src[bk] - p.id_offset) / p.id_stride;
-    q = p.q_ist + ((long long)b * kP + (ty * 16 + tx)) * kIstC;
-    t = p.bank_ist + (((long long)p.q_obj[b] * p.T + lid) * kP + (sy * 16 + sx)) * kIstC;
-  }
+  if (r >= *p.row_count || r >= max_rows) return;
+  const int flat = p.row_ids[r];                              // (b, k, t) of this valid correspondence
+  const int bk = flat >> 8, b = bk / p.k;
+  const long long tx = p.tar_pts[2 * (size_t)flat], ty = p.tar_pts[2 * (size_t)flat + 1];
+  const long long sx = p.src_pts[2 * (size_t)flat], sy = p.src_pts[2 * (size_t)flat + 1];
+  const long long lid = (p.id_src[bk] - p.id_offset) / p.id_stride;
+  const float* q = p.q_ist + ((long long)b * kP + (ty * 16 + tx)) * kIstC;
+  const float* t = p.bank_ist + (((long long)p.q_obj[b] * p.T + lid) * kP + (sy * 16 + sx)) * kIstC;
 #pragma unroll
   for (int part = 0; part < 2; ++part) {                  // columns [0,256) = query descriptor, [256,512) = template descriptor
     const float* src = part ? t : q;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int c = (lane + 32 * i) * 4;
-      float4 v = valid ? *reinterpret_cast<const float4*>(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 v = *reinterpret_cast<const float4*>(src + c);
       const float x[4] = {v.x, v.y, v.z, v.w};
       // IEEE fp16 hi / lo: 22 significant bits for these O(1) descriptors (bf16 pairs carry 16), same tensor rate
       __half h[4], l[4];
@@ -197,7 +193,7 @@ mlp_gather_planes_kernel(IstMlpParams p, __half* __restrict__ a_hi, __half* __re
         h[j] = __float2half_rn(xs);
         l[j] = __float2half_rn(xs - __half2float(h[j]));
       }
-      const size_t o = (size_t)row * 512 + part * 256 + c;
+      const size_t o = (size_t)r * 512 + part * 256 + c;
       *reinterpret_cast<uint2*>(a_hi + o) = make_uint2((uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
                                                        (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
       *reinterpret_cast<uint2*>(a_lo + o) = make_uint2((uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
@@ -206,23 +202,20 @@ mlp_gather_planes_kernel(IstMlpParams p, __half* __restrict__ a_hi, __half* __re
   }
 }
 
-// last layers on dense rows (row = flat (b,k,t)): one warp per row, fp32
+// last layers on the compacted rows: one warp per row, fp32, scattered back to (b,k,t)
 __global__ void __launch_bounds__(256)
-mlp_head_rows_kernel(IstMlpParams p, IstMlpWeights w, const float* __restrict__ h2s, const float* __restrict__ h2i, int total) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+mlp_head_rows_kernel(IstMlpParams p, IstMlpWeights w, const float* __restrict__ h2s, const float* __restrict__ h2i, int max_rows) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= total) return;
-  const bool valid = p.src_pts[2 * (size_t)row] != -1 && p.src_pts[2 * (size_t)row + 1] != -1;
+  if (r >= *p.row_count || r >= max_rows) return;
+  const float* hs = h2s + (size_t)r * 256;
+  const float* hi = h2i + (size_t)r * 256;
   float s = 0.f, c0 = 0.f, c1 = 0.f;
-  if (valid) {
-    const float* hs = h2s + (size_t)row * 256;
-    const float* hi = h2i + (size_t)row * 256;
-    for (int i = lane; i < 256; i += 32) {
-      s = fmaf(hs[i], w.s_w3[i], s);
-      const float v = hi[i];
-      c0 = fmaf(v, w.i_w3[i], c0);
-      c1 = fmaf(v, w.i_w3[256 + i], c1);
-    }
+  for (int i = lane; i < 256; i += 32) {
+    s = fmaf(hs[i], w.s_w3[i], s);
+    const float v = hi[i];
+    c0 = fmaf(v, w.i_w3[i], c0);
+    c1 = fmaf(v, w.i_w3[256 + i], c1);
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
@@ -231,17 +224,14 @@ mlp_head_rows_kernel(IstMlpParams p, IstMlpWeights w, const float* __restrict__ 
     c1 += __shfl_xor_sync(0xffffffffu, c1, off);
   }
   if (lane == 0) {
-    if (valid) {
-      s += w.s_b3[0];
-      c0 += w.i_b3[0];
-      c1 += w.i_b3[1];
-      if (w.use_tanh) { c0 = tanhf(c0); c1 = tanhf(c1); }
-    } else {
-      s = c0 = c1 = -1000.0f;                               // ist_net.py:110-113
-    }
-    p.rel_scale[row] = s;
-    p.rel_inplane[2 * (size_t)row] = c0;
-    p.rel_inplane[2 * (size_t)row + 1] = c1;
+    const int flat = p.row_ids[r];
+    s += w.s_b3[0];
+    c0 += w.i_b3[0];
+    c1 += w.i_b3[1];
+    if (w.use_tanh) { c0 = tanhf(c0); c1 = tanhf(c1); }
+    p.rel_scale[flat] = s;
+    p.rel_inplane[2 * (size_t)flat] = c0;
+    p.rel_inplane[2 * (size_t)flat + 1] = c1;
   }
 }
 
@@ -250,6 +240,9 @@ mlp_head_rows_kernel(IstMlpParams p, IstMlpWeights w, const float* __restrict__ 
 cudaError_t launch_mlp_gather_planes(const IstMlpParams& p, uint16_t* a_hi, uint16_t* a_lo, cudaStream_t stream) {
   const int total = p.B * p.k * kP;
   if (total <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(p.row_count, 0, sizeof(int), stream);
+  if (e != cudaSuccess) return e;
+  mlp_compact_kernel<<<(total + 255) / 256, 256, 0, stream>>>(p, total);          // row_ids, row_count, -1000 fill
   mlp_gather_planes_kernel<<<(total + 7) / 8, 256, 0, stream>>>(p, reinterpret_cast<__half*>(a_hi),
                                                                reinterpret_cast<__half*>(a_lo), total);
   return cudaGetLastError();

@@ -99,7 +99,8 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   const int passes = p.passes;
   const int bn = p.bn > 0 ? p.bn : kBN;                     // 128 / 192 / 256 output columns per tile
   const uint32_t idesc = umma_idesc_f16(kTileM, bn, p.f16 ? 0 : 1);   // A / B formats: bf16 (1) or fp16 (0) hi / lo planes
-  const int num_m = (p.M + kTileM - 1) / kTileM, num_n = p.N / bn;
+  const int M_rows = p.m_dev ? min(*p.m_dev, p.M) : p.M;    // data-dependent row count (IST regressor): read on the device
+  const int num_m = (M_rows + kTileM - 1) / kTileM, num_n = p.N / bn;
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;     // 0 = leader of the pair
   const int first_tile = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -233,7 +234,7 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       named_barrier_sync(1, kEpiWarps * 32);
       const float* sb = tail.bias_s[acc] + ch * half_cols;
       const float* sg = tail.gamma_s[acc] + ch * half_cols;
-      const bool row_ok = m < p.M;
+      const bool row_ok = m < M_rows;
       size_t out_row = (size_t)m;
       const float* pos_row = nullptr;
       if (p.mode == GEMM_PATCH_EMBED) {                // patch row -> token row (CLS first), + positional table

@@ -168,7 +168,6 @@ class ShardedRetriever:
         self._graphs = {}
         self.use_cuda_graph = False
         self._copy_stream = None
-        self._comm_stream = None
         self._ring = {"slot": 0, "bufs": {}}
 
     # ---- per-batch buffers (allocated once per batch size; nothing is allocated or zero-filled per step)
@@ -201,24 +200,15 @@ class ShardedRetriever:
         if n > 0:
             tok[r * per: r * per + n].copy_(self.model.ae_net.patch_tokens(tar_img_window))
         mark("a1_vit")
-        gathered = None
-        if G > 1:
-            # the descriptor all-gather (mostly waiting for the slowest rank's ViT) runs on a side stream behind the ViT
-            # and overlaps this rank's IST trunk; the search waits for it
-            cur = torch.cuda.current_stream(self.device)
-            if self._comm_stream is None:
-                self._comm_stream = torch.cuda.Stream(device=self.device)
-            self._comm_stream.wait_stream(cur)
-            with torch.cuda.stream(self._comm_stream):
-                eng.allgather(tok[r * per: (r + 1) * per], tok)
-                gathered = torch.cuda.Event()
-                gathered.record(self._comm_stream)
         if n > 0:
             ist = self.model.ist_net.forward_by_chunk(tar_img_window)
         mark("a6_ist_backbone")
-        if gathered is not None:
-            torch.cuda.current_stream(self.device).wait_event(gathered)
-        mark("wait_allgather_query_descriptors")
+        if G > 1:
+            # (issuing this all-gather on a side stream behind the ViT, overlapping the IST trunk, was measured: no gain in
+            # `value`, and e2e fell 2530 -> 1933 det/s at N = 2 -- the spinning NCCL CTAs hold SMs that the trunk's
+            # one-CTA-per-SM persistent kernels need, which couples this rank's trunk to the slowest rank's ViT)
+            eng.allgather(tok[r * per: (r + 1) * per], tok)
+        mark("allgather_query_descriptors")
         # a4 on the local descriptor shard -> light candidate records in this rank's slot, then THE collective + merge
         eng.set_queries(tok[:B], tar_mask, q_obj, norm_passes=1)
         eng.sim_candidates(out=buf["mine"])
