@@ -261,10 +261,11 @@ class CpuReference:
     fresh IST backbone pass over all crops for each of the k hypotheses (gigaPose.py:552-553);  "fair" = the same
     arithmetic with the backbone run once and the IST bank gathered once."""
 
-    def __init__(self, T, n_det=32, n_obj=8, k=5):
+    def __init__(self, T, n_det=32, n_obj=8, k=5, device="cpu"):
         from gigapose_b200 import synth
         from oracle import port
         self.port, self.k, self.T = port, k, T
+        self.device = torch.device(device)
         gc = torch.Generator().manual_seed(4242)
         labels = torch.randint(1, n_obj + 1, (n_det,), generator=gc)
         case = synth.make_feature_case(B=n_det, O=n_obj, T=T, seed=77, labels=labels, obj_chunk=1)
@@ -280,6 +281,12 @@ class CpuReference:
         self.rgb = synth.make_crops(n_det, seed=78)[0]
         self.vit, self.backbone, self.reg = port.DinoV2Port(), port.ISTBackbonePort(), port.RegressorPort()
         self.n_det, self.n_obj = n_det, n_obj
+        if self.device.type != "cpu":          # --gpu-eager-baseline: the same eager torch code on the B200 (cuBLAS / cuDNN)
+            for name in ("ae_features", "masks", "ist_features", "tar_feat", "tar_mask", "tar_ist", "rgb"):
+                setattr(self, name, getattr(self, name).to(self.device))
+            self.case = case.to(self.device)
+            for m in (self.vit, self.backbone, self.reg):
+                m.to(self.device)
 
     @torch.no_grad()
     def run(self, variant="fair", n=None):
@@ -288,9 +295,14 @@ class CpuReference:
         n = n or self.n_det
         c = self.case
         st = {}
+        on_gpu = self.device.type != "cpu"
+        if on_gpu:
+            torch.cuda.synchronize()
         t_all = time.perf_counter()
 
         def tic(name, t0):
+            if on_gpu:
+                torch.cuda.synchronize()
             st[name] = st.get(name, 0.0) + time.perf_counter() - t0
 
         t0 = time.perf_counter(); _ = port.ae_features(self.vit, self.rgb[:n]); tic("a1_vit", t0)
@@ -303,9 +315,9 @@ class CpuReference:
         pred = port.similarity_search(src_feats, self.tar_feat[:n], src_masks, self.tar_mask[:n], k=k)
         tic("a4_similarity_topk", t0)
         del src_feats, src_masks
-        rel_scale = torch.zeros(n, k, 256)
-        rel_inpl = torch.zeros(n, k, 256, 2)
-        bi = torch.arange(n)
+        rel_scale = torch.zeros(n, k, 256, device=self.device)
+        rel_inpl = torch.zeros(n, k, 256, 2, device=self.device)
+        bi = torch.arange(n, device=self.device)
         src_ist = None
         for kk in range(k):                                                      # gigaPose.py:545-575
             if variant == "as_written" or kk == 0:
@@ -326,6 +338,12 @@ class CpuReference:
         _ = port.pose_recovery(c.q_label[:n], c.q_K[:n], c.q_M[:n], ids, Ms.clone(), c.bank_K, c.bank_M, c.bank_poses)
         tic("a8_a9_sort_pose", t0)
         return time.perf_counter() - t_all, st
+
+    def run_on_device(self, variant="fair"):
+        """`run` with torch's factory functions defaulting to this reference's device (the port creates index tensors
+        with bare torch.arange / torch.zeros, exactly like the reference)."""
+        with torch.device(self.device):
+            return self.run(variant)
 
     def sweep_threads(self, cands, n):
         """Fastest thread count for the whole chain on the first `n` detections (more threads are not always faster for
@@ -362,6 +380,9 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch the per-batch kernel sequence eagerly")
+    ap.add_argument("--gpu-eager-baseline", action="store_true",
+                    help="also time the reference's eager PyTorch code (oracle port) on the SAME GPU (cuBLAS / cuDNN fp32): context "
+                         "for the hand-written kernels, SURVEY section 2")
     ap.add_argument("--profile-range", action="store_true",
                     help="wrap ONE extra resident step in cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -569,6 +590,24 @@ def main():
                     "ms_per_step": e2e_ms},
             "gpu_launches": int(launches), "roofline": roofline, "roofline_dominant": roofline_vit, "stage_ms": stage_ms}
     line["config"]["cuda_graph"] = bool(model.use_cuda_graph)
+    if args.gpu_eager_baseline:
+        torch.backends.cuda.matmul.allow_tf32 = False          # the reference's fp32 (trainer.precision: 32)
+        torch.backends.cudnn.allow_tf32 = False
+        n_det, n_obj = sample_shape(cfg)
+        del model, eng
+        torch.cuda.empty_cache()
+        ref_gpu = CpuReference(cfg["T"], n_det=n_det, n_obj=n_obj, device=device)
+        ref_gpu.run_on_device("fair")
+        runs = [ref_gpu.run_on_device("fair") for _ in range(3)]
+        t_best, st_best = min(runs, key=lambda r: r[0])
+        t_aw, st_aw = ref_gpu.run_on_device("as_written")
+        line["gpu_eager_baseline"] = dict(value=n_det / t_best, unit=UNIT, device=torch.cuda.get_device_name(device),
+                                          what="the reference's eager PyTorch code path (oracle port) on this GPU, fp32 (TF32 off), "
+                                               f"{n_det} detections, 'fair' variant, best of 3",
+                                          stage_s={kk: round(v, 5) for kk, v in st_best.items()},
+                                          as_written=dict(value=n_det / t_aw, stage_s={kk: round(v, 5) for kk, v in st_aw.items()}))
+        del ref_gpu
+        torch.cuda.empty_cache()
     if not args.no_cpu_baseline:
         # the CPU restatement of the reference on this box's host cores: thread count from a sweep on 4 detections, then
         # ONE pass over the bounded sample (the full c2 batch) with per-stage times

@@ -73,6 +73,8 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
 __device__ long long g_gemm_stamp[64];
 #define GSTAMP(i) do { if (blockIdx.x == 0 && p.N == 3072 && (i) < 64) g_gemm_stamp[i] = clock64(); } while (0)
 
+// kMode (GemmMode) is a template parameter: every layer type gets its own epilogue without the other modes' predicated
+// code and registers (the shared runtime-mode epilogue needed 168 registers and ~35 instructions per output element).
 // kSwap = false: rows of C are activation rows (tokens / output pixels), columns are output features.
 // kSwap = true (convolutions with 128 output channels): the roles are exchanged -- the 128-row UMMA operand is the
 // filter bank [128, K] and the 256-row operand is a tile of 256 output pixels, so that the tensor pipe still runs
@@ -82,7 +84,7 @@ __device__ long long g_gemm_stamp[64];
 // each CTA stages its own 128 rows of A and bn/2 rows of W, the even CTA issues the M = 256 instructions, every CTA
 // drains its own 128 accumulator rows.  Per SM the tensor core then reads 4 KB + 4 KB of operands per 128-cycle
 // instruction instead of 4 KB + 8 KB, which is what the shared-memory pipe could not sustain next to the epilogue.
-template <bool kSwap, bool kPair>
+template <bool kSwap, bool kPair, int kMode>
 __global__ void __launch_bounds__(kThreads, 1)
 vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, GemmParams p) {
@@ -229,7 +231,7 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       // stage the per-column vectors of this tile (256 epilogue threads, one column each)
       if (!kSwap && etid < bn) {
         tail.bias_s[acc][etid] = __ldg(p.bias + ntile0 + etid);
-        if (p.mode == GEMM_SCALE_RESIDUAL) tail.gamma_s[acc][etid] = __ldg(p.gamma + ntile0 + etid);
+        if (kMode == GEMM_SCALE_RESIDUAL) tail.gamma_s[acc][etid] = __ldg(p.gamma + ntile0 + etid);
       }
       named_barrier_sync(1, kEpiWarps * 32);
       const float* sb = tail.bias_s[acc] + ch * half_cols;
@@ -237,7 +239,7 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       const bool row_ok = m < M_rows;
       size_t out_row = (size_t)m;
       const float* pos_row = nullptr;
-      if (p.mode == GEMM_PATCH_EMBED) {                // patch row -> token row (CLS first), + positional table
+      if (kMode == GEMM_PATCH_EMBED) {                // patch row -> token row (CLS first), + positional table
         const int img = m / p.patches_per_img, pp = m - img * p.patches_per_img;
         out_row = (size_t)img * p.tokens_per_img + 1 + pp;
         pos_row = p.pos + (size_t)(1 + pp) * p.N;
@@ -307,8 +309,8 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             v[j] += __uint_as_float((uint32_t)*reinterpret_cast<const uint16_t*>(stg + j * 80 + lane * 2) << 16);
           __syncwarp();
         };
-        if (p.mode == GEMM_PLANES_ADD_RELU) { rows_in(p.res_hi); rows_in(p.res_lo); }
-        if (p.mode == GEMM_PLANES_RELU || p.mode == GEMM_PLANES_ADD_RELU) {
+        if (kMode == GEMM_PLANES_ADD_RELU) { rows_in(p.res_hi); rows_in(p.res_lo); }
+        if (kMode == GEMM_PLANES_RELU || kMode == GEMM_PLANES_ADD_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
@@ -339,10 +341,10 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           v[j] = (p.acc_scale != 0.f ? __uint_as_float(v32[j]) * p.acc_scale : __uint_as_float(v32[j])) + sb[c0 + j];
-        if (p.mode == GEMM_PLANES || p.mode == GEMM_PLANES_GELU || p.mode == GEMM_QKV_HEADS || p.mode == GEMM_PLANES_RELU ||
-            p.mode == GEMM_PLANES_ADD_RELU) {
+        if (kMode == GEMM_PLANES || kMode == GEMM_PLANES_GELU || kMode == GEMM_QKV_HEADS || kMode == GEMM_PLANES_RELU ||
+            kMode == GEMM_PLANES_ADD_RELU) {
           uint32_t hi[16], lo[16];
-          if (p.mode == GEMM_PLANES_ADD_RELU) {          // BasicBlock: relu(shortcut + bn2(conv2(.)))   (resnet.py:45-50)
+          if (kMode == GEMM_PLANES_ADD_RELU) {          // BasicBlock: relu(shortcut + bn2(conv2(.)))   (resnet.py:45-50)
             const size_t rb = (out_row * p.N + n) * 2;
             load_rows_64B(hi, reinterpret_cast<const uint8_t*>(p.res_hi), rb);
             load_rows_64B(lo, reinterpret_cast<const uint8_t*>(p.res_lo), rb);
@@ -355,8 +357,8 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             float a = v[j], b = v[j + 1];
-            if (p.mode == GEMM_PLANES_GELU) { a = gelu_erf(a); b = gelu_erf(b); }
-            if (p.mode == GEMM_PLANES_RELU || p.mode == GEMM_PLANES_ADD_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+            if (kMode == GEMM_PLANES_GELU) { a = gelu_erf(a); b = gelu_erf(b); }
+            if (kMode == GEMM_PLANES_RELU || kMode == GEMM_PLANES_ADD_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
             if (p.f16) {                             // saturating: a value beyond the fp16 range stays finite (and wrong) instead of inf
               a = fminf(fmaxf(a, -65504.f), 65504.f);
               b = fminf(fmaxf(b, -65504.f), 65504.f);
@@ -371,14 +373,14 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             }
           }
           size_t dst = out_row * p.N + n;
-          if (p.mode == GEMM_QKV_HEADS) {   // head-major: [q|k|v][crop][head][token][64] so that attention tiles are contiguous
+          if (kMode == GEMM_QKV_HEADS) {   // head-major: [q|k|v][crop][head][token][64] so that attention tiles are contiguous
             const int which = n >> 10, head = (n & 1023) >> 6, d0 = n & 63;
             const int img = m / p.tokens_per_img, tok = m - img * p.tokens_per_img;
             dst = ((((size_t)which * p.qkv_crop_stride + img) * 16 + head) * p.tokens_per_img + tok) * 64 + d0;
           }
           store_rows_64B(hi, reinterpret_cast<uint8_t*>(p.out_hi), dst * 2);
           store_rows_64B(lo, reinterpret_cast<uint8_t*>(p.out_lo), dst * 2);
-        } else if (p.mode == GEMM_SCALE_RESIDUAL) {      // x += gamma * (acc + bias)   (blocks: ls1 / ls2 + residual)
+        } else if (kMode == GEMM_SCALE_RESIDUAL) {      // x += gamma * (acc + bias)   (blocks: ls1 / ls2 + residual)
           const size_t rowb = (out_row * p.N + n) * 4;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -389,9 +391,9 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
               w[j] = __float_as_uint(__uint_as_float(w[j]) + sg[c0 + half * 16 + j] * v[half * 16 + j]);
             store_rows_64B(w, reinterpret_cast<uint8_t*>(p.x), rowb + half * 64);
           }
-        } else if (p.mode == GEMM_ROWS_F32 || p.mode == GEMM_ROWS_F32_RELU) {   // plain fp32 rows (last 1x1 convolution of the IST
+        } else if (kMode == GEMM_ROWS_F32 || kMode == GEMM_ROWS_F32_RELU) {   // plain fp32 rows (last 1x1 convolution of the IST
           const size_t rowb = (out_row * p.N + n) * 4;                          // trunk; second hidden layer of the IST MLP)
-          const float floor_v = p.mode == GEMM_ROWS_F32_RELU ? 0.f : -INFINITY;
+          const float floor_v = kMode == GEMM_ROWS_F32_RELU ? 0.f : -INFINITY;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t w[16];
@@ -462,16 +464,23 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 
 cudaError_t read_gemm_stamps(long long* host64) { return cudaMemcpyFromSymbol(host64, g_gemm_stamp, sizeof(long long) * 64); }
 
-cudaError_t launch_vit_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
-                            const CUtensorMap& w_lo, const GemmParams& p, int num_sms, cudaStream_t stream) {
-  static bool configured = false;
+namespace {
+template <bool kSwap, bool kPair, int kMode>
+cudaError_t launch_mode(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
+                        const GemmParams& p, int grid, int cluster, cudaStream_t stream) {
+  static bool configured = false;                  // one flag per instantiation
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(vit_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(vit_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(vit_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(vit_gemm_kernel<kSwap, kPair, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
+  return launch_ex(vit_gemm_kernel<kSwap, kPair, kMode>, dim3(grid), dim3(kThreads), kSmemBytes, stream, cluster, true, a_hi, a_lo,
+                   w_hi, w_lo, p);
+}
+}  // namespace
+
+cudaError_t launch_vit_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                            const CUtensorMap& w_lo, const GemmParams& p, int num_sms, cudaStream_t stream) {
   if (p.M <= 0) return cudaSuccess;
   const int bn = p.bn > 0 ? p.bn : kBN;
   if ((bn != 128 && bn != 192 && bn != 256) || p.N % bn != 0 || p.K % kBlockK != 0) return cudaErrorInvalidValue;
@@ -480,17 +489,47 @@ cudaError_t launch_vit_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, co
   if (p.swap && (p.pair || bn != kBN || p.M % kBM != 0 ||
                  (p.mode != GEMM_PLANES && p.mode != GEMM_PLANES_RELU && p.mode != GEMM_PLANES_ADD_RELU)))
     return cudaErrorInvalidValue;
+#define GP_GEMM_CASE(SWAP, PAIR, MODE) \
+  case MODE: return launch_mode<SWAP, PAIR, MODE>(a_hi, a_lo, w_hi, w_lo, p, grid, PAIR ? 2 : 1, stream);
   if (p.pair) {                                   // one 2-CTA cluster per 256 x bn tile
     if (p.conv && p.M % (2 * kBM) != 0) return cudaErrorInvalidValue;
     const int tiles = ((p.M + 2 * kBM - 1) / (2 * kBM)) * (p.N / bn);
-    const int clusters = tiles < num_sms / 2 ? tiles : num_sms / 2;
-    return launch_ex(vit_gemm_kernel<false, true>, dim3(2 * clusters), dim3(kThreads), kSmemBytes, stream, 2, true, a_hi, a_lo,
-                     w_hi, w_lo, p);
+    const int grid = 2 * (tiles < num_sms / 2 ? tiles : num_sms / 2);
+    switch (p.mode) {
+      GP_GEMM_CASE(false, true, GEMM_QKV_HEADS)
+      GP_GEMM_CASE(false, true, GEMM_SCALE_RESIDUAL)
+      GP_GEMM_CASE(false, true, GEMM_PLANES_GELU)
+      GP_GEMM_CASE(false, true, GEMM_PLANES_RELU)
+      GP_GEMM_CASE(false, true, GEMM_PLANES_ADD_RELU)
+      GP_GEMM_CASE(false, true, GEMM_PLANES)
+      GP_GEMM_CASE(false, true, GEMM_ROWS_F32)
+      GP_GEMM_CASE(false, true, GEMM_ROWS_F32_RELU)
+      default: return cudaErrorInvalidValue;
+    }
   }
   const int tiles = ((p.M + kBM - 1) / kBM) * (p.N / bn);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  if (p.swap) return launch_ex(vit_gemm_kernel<true, false>, dim3(grid), dim3(kThreads), kSmemBytes, stream, 1, true, a_hi, a_lo, w_hi, w_lo, p);
-  return launch_ex(vit_gemm_kernel<false, false>, dim3(grid), dim3(kThreads), kSmemBytes, stream, 1, true, a_hi, a_lo, w_hi, w_lo, p);
+  if (p.swap) {
+    switch (p.mode) {
+      GP_GEMM_CASE(true, false, GEMM_PLANES)
+      GP_GEMM_CASE(true, false, GEMM_PLANES_RELU)
+      GP_GEMM_CASE(true, false, GEMM_PLANES_ADD_RELU)
+      default: return cudaErrorInvalidValue;
+    }
+  }
+  switch (p.mode) {
+    GP_GEMM_CASE(false, false, GEMM_PLANES)
+    GP_GEMM_CASE(false, false, GEMM_PLANES_GELU)
+    GP_GEMM_CASE(false, false, GEMM_SCALE_RESIDUAL)
+    GP_GEMM_CASE(false, false, GEMM_PATCH_EMBED)
+    GP_GEMM_CASE(false, false, GEMM_QKV_HEADS)
+    GP_GEMM_CASE(false, false, GEMM_PLANES_RELU)
+    GP_GEMM_CASE(false, false, GEMM_PLANES_ADD_RELU)
+    GP_GEMM_CASE(false, false, GEMM_ROWS_F32)
+    GP_GEMM_CASE(false, false, GEMM_ROWS_F32_RELU)
+    default: return cudaErrorInvalidValue;
+  }
+#undef GP_GEMM_CASE
 }
 
 }  // namespace gp
