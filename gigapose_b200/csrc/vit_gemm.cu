@@ -426,21 +426,29 @@ vit_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           else mbar_arrive(&tail.tmem_empty_bar[acc]);
         }
       };
-      // (a real loop over chunk pairs: `process` is instantiated twice instead of once per chunk position and branch -- the
-      // fully unrolled epilogue was 75 - 150 KB of SASS per kernel and 30 - 44 % of its stall samples were instruction fetch)
+      // (a rolled loop over chunk pairs -- `process` instantiated twice instead of six times, SASS 152 -> 64 KB for the GELU
+      // kernel -- was measured too: per-kernel times under ncu 7 % WORSE (qkv 101 -> 115 us), step time unchanged; not kept)
       tmem_ld_32x32(taddr, va);
       tmem_ld_wait_for(va);
-#pragma unroll 1
-      for (int c = 0; c < nchunks; c += 2) {
-        const bool has_b = c + 1 < nchunks;
-        if (has_b) tmem_ld_32x32(taddr + 32 * (c + 1), vb); else release_acc();       // va holds the last chunk
-        process(va, 32 * c);
-        if (has_b) {
+      tmem_ld_32x32(taddr + 32, vb);
+      process(va, 0);
+      tmem_ld_wait_for(vb);
+      if (nchunks == 2) {
+        release_acc();
+        process(vb, 32);
+      } else {
+        tmem_ld_32x32(taddr + 64, va);
+        process(vb, 32);
+        tmem_ld_wait_for(va);
+        if (nchunks == 3) {
+          release_acc();
+          process(va, 64);
+        } else {
+          tmem_ld_32x32(taddr + 96, vb);
+          process(va, 64);
           tmem_ld_wait_for(vb);
-          const bool more = c + 2 < nchunks;
-          if (more) tmem_ld_32x32(taddr + 32 * (c + 2), va); else release_acc();     // vb holds the last chunk
-          process(vb, 32 * (c + 1));
-          if (more) tmem_ld_wait_for(va);
+          release_acc();
+          process(vb, 96);
         }
       }
       if (e == 0 && lane == 0) GSTAMP(unit * 4 + 3);
