@@ -74,12 +74,13 @@ __device__ __forceinline__ float2 ld_pair_sw128(const uint8_t* hi, const uint8_t
 __device__ long long g_attn_stamp[32];
 #define STAMP(i) do { if (blockIdx.x == (gridDim.x > 300 ? 300u : 0u)) g_attn_stamp[i] = clock64(); } while (0)
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <int kPasses>        // 3 = fp32-faithful split products, 1 = plain bf16 (a template parameter: the other mode's code
+__global__ void __launch_bounds__(kThreads, 1)   // and registers stay out of the instruction stream)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_128, const __grid_constant__ CUtensorMap tm_lo_128,
                     const __grid_constant__ CUtensorMap tm_hi_16, const __grid_constant__ CUtensorMap tm_lo_16,
                     const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __restrict__ qkv_lo,
-                    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int crop_stride, int passes,
-                    int num_items) {
+                    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int crop_stride, int num_items) {
+  constexpr int passes = kPasses;
   extern __shared__ uint8_t smem_raw[];
   pdl_trigger();
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -441,7 +442,8 @@ cudaError_t launch_attention_tc(const CUtensorMap& hi128, const CUtensorMap& lo1
                                 uint16_t* out_lo, int b, int crop_stride, int passes, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -453,9 +455,12 @@ cudaError_t launch_attention_tc(const CUtensorMap& hi128, const CUtensorMap& lo1
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int items = b * kHeads;
-  return launch_ex(attention_tc_kernel, dim3(items < num_sms ? items : num_sms), dim3(kThreads), kSmem, s, 1, true, hi128, lo128,
-                   hi16, lo16, reinterpret_cast<const __nv_bfloat16*>(qkv_hi), reinterpret_cast<const __nv_bfloat16*>(qkv_lo),
-                   reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), crop_stride, passes, items);
+  const dim3 grid(items < num_sms ? items : num_sms);
+  auto qh = reinterpret_cast<const __nv_bfloat16*>(qkv_hi), ql = reinterpret_cast<const __nv_bfloat16*>(qkv_lo);
+  auto oh = reinterpret_cast<__nv_bfloat16*>(out_hi), ol = reinterpret_cast<__nv_bfloat16*>(out_lo);
+  if (passes == 3)
+    return launch_ex(attention_tc_kernel<3>, grid, dim3(kThreads), kSmem, s, 1, true, hi128, lo128, hi16, lo16, qh, ql, oh, ol, crop_stride, items);
+  return launch_ex(attention_tc_kernel<1>, grid, dim3(kThreads), kSmem, s, 1, true, hi128, lo128, hi16, lo16, qh, ql, oh, ol, crop_stride, items);
 }
 
 }  // namespace gp
