@@ -387,7 +387,7 @@ def run_sharded_bench(args, cfg, config, wl_name, rank, world, device, METRIC, U
         torch.cuda.synchronize()
         return res
 
-    e2e_loop(2)
+    e2e_loop(6)                       # fills the pinned rings (a cudaHostAlloc inside the timed region stalls the host thread)
     dist.barrier()
     t0 = time.perf_counter()
     res = e2e_loop(args.steps)
