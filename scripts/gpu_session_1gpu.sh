@@ -1,4 +1,7 @@
 #!/bin/bash
+# One 1-GPU session: every -m gpu test in its own process, smoke(), the bench line (+ CPU and eager-GPU baselines), the ncu
+# launch list, one `--set full` capture of the similarity kernel, and the reference arm on the box's host cores.
+# (gpurun --timeout 3000 -- 'bash scripts/gpu_session_1gpu.sh'; outputs land in gpurun_out/)
 mkdir -p gpurun_out
 rm -f gpurun_out/tests.log
 bash scripts/gpu_check.sh > /dev/null 2>&1

@@ -1,4 +1,6 @@
 #!/bin/bash
+# One 8-GPU box: c4 at N = 8, c3 at N = 4, c2 at N = 2 and N = 1, back to back (gpurun --gpus 8 -- 'bash scripts/gpu_session_8gpu.sh').
+# Add `--workload c5` to the first line for BASELINE configs[4].
 mkdir -p gpurun_out
 L=gpurun_out/run_n8b.log
 : > $L

@@ -21,7 +21,16 @@ class ObjectPoseRecovery(torch.nn.Module):
         lib = _lib.load()
         dev = pred_M.device
         B, k = pred_src_views.shape
-        q_obj = (tar_label.to(dev) - 1).to(torch.int32).contiguous()
+        # this module-level entry point is not on the resident-bank hot path: validating the indices costs one small
+        # device->host read (the reference would raise an IndexError from its advanced indexing, poses.py:111-116)
+        O, T = self.template_Ms.shape[:2]
+        lab = tar_label.to(dev).long() - 1
+        views = pred_src_views.to(dev).long()
+        bounds = torch.stack([lab.min(), lab.max(), views.min(), views.max()]).tolist() if B * k else [0, 0, 0, 0]
+        if bounds[0] < 0 or bounds[1] >= O or bounds[2] < 0 or bounds[3] >= T:
+            raise IndexError(f"forward_recovery: object labels must lie in [1, {O}] and template ids in [0, {T}); got labels "
+                             f"[{bounds[0] + 1}, {bounds[1] + 1}], template ids [{bounds[2]}, {bounds[3]}]")
+        q_obj = lab.to(torch.int32).contiguous()
         tar_K, tar_M = tar_K.to(dev).float().contiguous(), tar_M.to(dev).float().contiguous()
         ids, M = pred_src_views.to(dev).long().contiguous(), pred_M.float().contiguous()
         tK, tM, tP = (t.to(dev) for t in (self.template_K, self.template_Ms, self.template_poses))
