@@ -151,3 +151,51 @@ def test_detection_windows_and_light_records():
     assert set(light) == set(multigpu.LIGHT_FIELDS) and "rel_scale" in full and n_light < n_full
     assert n_light == 4 * 5 * (4 + 4 + 256 * 4 + 256 + 256)            # 1544 B per candidate, no padding needed here
     assert all(off % 16 == 0 for off, _, _ in light.values())
+
+
+def test_bank_builder_streams_full_chunks_across_objects():
+    """Row f2 host logic: the onboarding builder feeds the encoders 64-crop chunks that straddle object boundaries and
+    writes every (object, template) slot exactly once, in order (encoders and engine are stand-ins: no GPU needed)."""
+    import torch
+    from src.models.gigaPose import _BankBuilder
+
+    class Enc:
+        def __init__(self):
+            self.calls = []
+
+        def raw_tokens(self, rgb):
+            self.calls.append(rgb.shape[0])
+            return rgb[:, :1, :1, 0].reshape(-1, 1, 1).repeat(1, 257, 1024)      # token value = crop id
+
+        def forward_by_chunk(self, rgb):
+            return rgb[:, :1, :1, :1].repeat(1, 256, 16, 16)
+
+    class Model:
+        pass
+
+    class Eng:
+        def __init__(self):
+            self.writes = []
+
+        def bank_write(self, obj, t0, tokens, mask, ist_feat=None, norm_passes=1):
+            assert norm_passes == 2 and tokens.shape[1:] == (257, 1024) and ist_feat.shape[1:] == (256, 16, 16)
+            ids = tokens[:, 0, 0].long().tolist()
+            assert ids == ist_feat[:, 0, 0, 0].long().tolist() == mask[:, 0, 0].long().tolist()
+            self.writes.append((obj, t0, ids))
+
+    model, eng = Model(), Eng()
+    model.ae_net = Enc()
+    model.ist_net = model.ae_net
+    b = _BankBuilder(model, eng, chunk=64)
+    O, T = 3, 70
+    for o in range(O):
+        ids = torch.arange(o * T, (o + 1) * T, dtype=torch.float32)
+        b.add(o, ids.view(T, 1, 1, 1).expand(T, 3, 4, 4), ids.view(T, 1, 1).expand(T, 4, 4))
+    b.flush()
+    assert model.ae_net.calls == [64, 64, 64, 18] and b.crops == O * T
+    seen = {}
+    for obj, t0, ids in eng.writes:
+        for j, cid in enumerate(ids):
+            assert (obj, t0 + j) not in seen
+            seen[(obj, t0 + j)] = cid
+    assert seen == {(o, t): o * T + t for o in range(O) for t in range(T)}
