@@ -599,6 +599,10 @@ def main():
                     "ms_per_step": e2e_ms},
             "gpu_launches": int(launches), "roofline": roofline, "roofline_dominant": roofline_vit, "stage_ms": stage_ms}
     line["config"]["cuda_graph"] = bool(model.use_cuda_graph)
+    # row f2: batched onboarding (both encoders over all O x T template crops in 64-crop chunks + bank writes), CUDA events
+    line["onboarding"] = {"s_per_object": round(getattr(model, "onboarding_s_per_object", float("nan")), 4),
+                          "templates_per_object": cfg["T"], "objects": cfg["O"],
+                          "note": "synthetic template crops already on the device; ViT-L/14 + IST trunk + bank write"}
     if args.gpu_eager_baseline:
         torch.backends.cuda.matmul.allow_tf32 = False          # the reference's fp32 (trainer.precision: 32)
         torch.backends.cudnn.allow_tf32 = False
