@@ -165,8 +165,6 @@ class ShardedRetriever:
         eng.set_poses(torch.stack(Ks).float(), torch.stack(Ms).float(), torch.stack(Ps).float())
         eng.set_ist_weights(model.ist_net.regressor)
         self._bufs = {}
-        self._graphs = {}
-        self.use_cuda_graph = False
         self._copy_stream = None
         self._ring = {"slot": 0, "bufs": {}}
 
@@ -229,32 +227,6 @@ class ShardedRetriever:
         mark("a7_a8_a9_ransac_sort_pose")
         return out
 
-    def retrieve_graphed(self, tar_img_window, tar_mask, q_obj, tar_K_window, tar_M_window):
-        """`retrieve` replayed as ONE CUDA graph per batch shape: the ~200 kernel launches AND the two in-library NCCL
-        all-gathers of a step are captured together (NCCL collectives are capturable; every rank replays the same
-        graph).  Outputs are copies of the graph's static tensors."""
-        key = (tar_img_window.shape[0], tar_mask.shape[0])
-        entry = self._graphs.get(key)
-        cur = torch.cuda.current_stream(self.device)
-        args = (tar_img_window, tar_mask, q_obj, tar_K_window, tar_M_window)
-        if entry is None:
-            static = [t.clone() for t in args]
-            side = torch.cuda.Stream(device=self.device)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                for _ in range(2):                                   # warm-up outside the capture (NCCL connections, buffers)
-                    self.retrieve(*static)
-            cur.wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                out = self.retrieve(*static)
-            entry = self._graphs[key] = (graph, static, out)
-        graph, static, out = entry
-        for dst, src in zip(static, args):
-            dst.copy_(src, non_blocking=True)
-        graph.replay()
-        return None if out is None else {k: v.clone() for k, v in out.items()}
-
     # ---- host <-> device pipelining (same contract as GigaPose.stage / fetch_async)
     def stage(self, batch):
         """Starts the upload of one pinned host batch on a copy stream: this rank's crop window + the full masks /
@@ -283,8 +255,7 @@ class ShardedRetriever:
         for t in staged.values():
             if torch.is_tensor(t):
                 t.record_stream(cur)
-        fn = self.retrieve_graphed if self.use_cuda_graph else self.retrieve
-        return fn(staged["img"], staged["mask"], staged["q_obj"], staged["K"], staged["M"])
+        return self.retrieve(staged["img"], staged["mask"], staged["q_obj"], staged["K"], staged["M"])
 
     def fetch_async(self, out):
         """Device -> pinned host copy of this rank's poses + scores; `.result()` waits for it."""
@@ -341,11 +312,10 @@ def run_sharded_bench(args, cfg, config, wl_name, rank, world, device, METRIC, U
     q_obj = (labels - 1).to(device)
     K, M = dev(batch_host.tar_K[lo:hi]), dev(batch_host.tar_M[lo:hi])
 
-    retr.use_cuda_graph = False       # measured at c4 / N = 8: 13.11 -> 13.01 ms with the step captured (kernels + NCCL); not
-                                      # worth a captured collective in the default path (process teardown must drop the graph first)
-
+    # (the step captured as one CUDA graph, kernels + both NCCL all-gathers, was measured at c4 / N = 8: 13.11 -> 12.95 ms,
+    # profiles/r02_bench_n8_c4_graph.json; not worth a captured collective in the default path, and the code was dropped)
     def step_resident():
-        return (retr.retrieve_graphed if retr.use_cuda_graph else retr.retrieve)(img, mask, q_obj, K, M)
+        return retr.retrieve(img, mask, q_obj, K, M)
 
     l0 = retr.eng.launch_count()
     retr.retrieve(img, mask, q_obj, K, M)                 # launches of this library per step, counted on one eager step
@@ -439,7 +409,7 @@ def run_sharded_bench(args, cfg, config, wl_name, rank, world, device, METRIC, U
                                                    "query descriptors + 1 all-gather of top-k records (in the library, "
                                                    "NCCL over NVLink)",
                                **{kk: (vv + ["e"] if kk == "native_rows" else vv) for kk, vv in bench.rows_config().items()},
-                               planted_view_in_topk=hit, cuda_graph=bool(retr.use_cuda_graph)),
+                               planted_view_in_topk=hit, cuda_graph=False),
                 "clocks": clocks.summary(),
                 "e2e": {"value": B / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms,
