@@ -605,8 +605,8 @@ int gp_ist_mlp(gp_handle_t h, int b0, int n, const float* q_ist, int ist_layout,
   }
   // tensor-core form: compacted valid rows (device-side count, no host sync) -> 512 -> [512 | 512] -> 256 + 256 -> heads.
   // Operands are IEEE fp16 hi / lo pairs (not bf16): descriptors, weights and hidden activations of this regressor are
-  // O(1e-2 .. 1e2), where an fp16 pair carries 22 significant bits -- the regressor outputs then agree with fp32 to ~5e-6
-  // (bf16 pairs: 4e-5, which moved a pose component by 1.2e-3 on the parity suite), at the same tensor rate.
+  // O(1e-2 .. 1e2), where an fp16 pair carries 22 significant bits -- the regressor outputs then agree with the fp32 SIMT
+  // kernels to 2e-5 (bf16 pairs: 4e-5, which moved a pose component by 1.2e-3 on the parity suite), at the same tensor rate.
   const int rows = n * c.top_k * GP_NUM_PATCHES;                      // a multiple of 256: whole pair tiles
   const uint64_t max_rows = (uint64_t)c.max_batch * c.top_k * GP_NUM_PATCHES;
   uint16_t* h1_hi = reinterpret_cast<uint16_t*>(h->ws.hidden1);

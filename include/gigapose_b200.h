@@ -102,7 +102,7 @@ int gp_bank_write_ist(gp_handle_t h, int obj, int tmpl0, int n, const float* ist
 int gp_bank_set_poses(gp_handle_t h, const float* K, const float* M, const float* poses, void* stream);
 
 /* IST regressor weights (ist_net.py:140-155), f32 device pointers in nn.Linear layout [out,in].  The two hidden layers
- * are packed into bf16 hi/lo planes on `stream` (tensor-core form); biases and the last layer are referenced in place
+ * are packed into IEEE fp16 hi/lo planes (weights x 64, undone in the GEMM epilogue) on `stream` (tensor-core form); biases and the last layer are referenced in place
  * (the caller keeps the tensors alive).  Order: scale {w1,b1,w2,b2,w3,b3}, inplane {w1,b1,w2,b2,w3,b3}. */
 int gp_set_ist_weights(gp_handle_t h, const float* const weights[12], int use_tanh, void* stream);
 
