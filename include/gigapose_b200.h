@@ -92,7 +92,8 @@ int gp_destroy(gp_handle_t h);
  *   ist_feat  f32  [n, 256, 16, 16] IST backbone features (gigaPose.py:376), may be NULL if a5 is not used */
 int gp_bank_write(gp_handle_t h, int obj, int tmpl0, int n, const float* feat, int feat_layout, int norm_passes,
                   const float* mask, int H, int W, const float* ist_feat, void* stream);
-/* IST features only: `n` templates of object `obj` starting at IST-bank slot `tmpl0` (a GLOBAL template id when
+/* IST features only (`template_data["ist_features"]`, gigaPose.py:375-376): `n` templates of object `obj` starting at
+ * IST-bank slot `tmpl0` (a GLOBAL template id when
  * cfg.ist_bank_global = 1).  ist_layout: GP_LAYOUT_CHANNEL_MAJOR [n,256,16,16] (ISTNet.forward_by_chunk's shape) or
  * GP_LAYOUT_PATCH_MAJOR [n,256 patches,256 channels] (what gp_ist_trunk_forward writes: stored as is). */
 int gp_bank_write_ist(gp_handle_t h, int obj, int tmpl0, int n, const float* ist_feat, int ist_layout, void* stream);
@@ -192,7 +193,9 @@ int gp_sort_and_pose(gp_handle_t h, int b0, int n, int sort_by_inliers, const fl
 /* --- row e: multi-GPU (no reference code: inference is single-GPU, configs/machine/trainer/local.yaml:4) ----------
  * One process per GPU; rank r holds the descriptor shard {tau : tau % world == r} (cfg.template_id_stride / offset). */
 /* Binds an NCCL communicator (an `ncclComm_t`, e.g. torch's ProcessGroupNCCL communicator) to the handle.  The NCCL
- * entry points are resolved from the already loaded libnccl at run time (no link-time dependency). */
+ * entry points are resolved from the already loaded libnccl at run time (no link-time dependency).  The communicator is
+ * BORROWED: it must stay alive for as long as gp_allgather / gp_topk_allgather_merge are called on this handle, and its
+ * rank / size must equal cfg.template_id_offset / cfg.template_id_stride. */
 int gp_comm_init(gp_handle_t h, void* nccl_comm, int rank, int world);
 /* ncclAllGather of `bytes_per_rank` bytes on `stream`: recv = [world][bytes_per_rank]; send may alias its own slot. */
 int gp_allgather(gp_handle_t h, const void* send, void* recv, size_t bytes_per_rank, void* stream);
