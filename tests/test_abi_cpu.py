@@ -69,3 +69,25 @@ def test_product_code_never_imports_the_oracle():
                     if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M):
                         offenders.append(os.path.join(dirpath, f))
     assert not offenders, offenders
+
+
+def test_abi_v2_config_and_argument_checks_need_no_gpu(lib):
+    """ABI 2: the replicated IST bank is sized by `ist_bank_global`; the multi-GPU and helper entry points reject bad
+    arguments through the status channel without touching a device."""
+    def sizes(**kw):
+        cfg = _lib.GpConfig(abi_version=_lib.GP_ABI_VERSION, device=0, num_objects=21, num_templates=21,
+                            num_templates_global=162, template_id_stride=8, template_id_offset=3, max_batch=128, top_k=5,
+                            sim_threshold=0.5, patch_threshold=3, pixel_threshold=14, patch_size=14, precision=0, **kw)
+        bank, ws = C.c_size_t(), C.c_size_t()
+        rc = lib.gp_query_sizes(C.byref(cfg), C.byref(bank), C.byref(ws))
+        return rc, bank.value, ws.value
+    rc0, bank_local, ws0 = sizes(ist_bank_global=0)
+    rc1, bank_global, ws1 = sizes(ist_bank_global=1)
+    assert rc0 == 0 and rc1 == 0 and ws0 == ws1
+    extra = 21 * (162 - 21) * 256 * 256 * 4                       # the other shards' IST features, f32 patch-major
+    assert extra <= bank_global - bank_local < extra + 4096
+    assert sizes(ist_bank_global=2)[0] == -1 and b"ist_bank_global" in lib.gp_last_error()
+    assert lib.gp_comm_init(None, None, 0, 1) == -1
+    assert lib.gp_allgather(None, None, None, 0, None) == -1
+    assert lib.gp_normalize_patch_tokens(0, None, None, None) == -1
+    assert lib.gp_bank_write_ist(None, 0, 0, 1, None, 0, None) == -1
